@@ -1,0 +1,180 @@
+// bro_parse.cuh -- match scoring and the greedy+lazy parse of one parse unit (one GPU thread per unit).
+//
+// Reference semantics: FindLongestMatch scoring (backward_references/mod.rs:1871-1889, 1151-1154; H9 :657-708)
+// and CreateBackwardReferences (mod.rs:2376-2552).  B200 re-design: the hash-bucket walk is NOT done here --
+// the match kernel has already produced, for every position, the best bucket candidate (best[p] =
+// distance << 8 | min(len, LCAP)) in parallel; the serial part left is the last-distance probes, lazy
+// deferral, and command emission, over a unit of a few KiB with a unit-local distance cache.
+#pragma once
+#include "bro_common.cuh"
+
+namespace bro {
+
+struct EncParams {
+  int quality;        // 5..9
+  int lgwin;          // 10..24
+  int hash_type;      // 5, 6 or 9 (encode.rs:834-893)
+  int key_bits;       // bucket_bits
+  int hash_len;       // 4 or 5 bytes hashed
+  int depth;          // bucket depth = 1 << block_bits
+  int n_last;         // num_last_distances_to_check
+  uint32_t lcap;      // per-position match length cap of the match kernel (<= 255)
+  uint32_t unit;      // parse unit size in bytes
+  uint32_t mb_units;  // parse units per metablock
+  uint32_t max_backward;  // (1 << lgwin) - 16
+  uint32_t n;         // input size
+  uint32_t size_hint;
+  int use_rle_opt;    // apply BrotliOptimizeHuffmanCountsForRle
+  int split;          // greedy block splitting on/off
+  int ctx_model;      // literal context modelling on/off
+};
+
+// ---- scores ----
+BRO_HD uint32_t score_regular(int hash_type, uint32_t len, uint32_t backward) {
+  if (hash_type == 9) return (7680u + 540u * len - 120u * log2_floor_nz(backward)) >> 2;
+  return 1920u + 135u * len - 30u * log2_floor_nz(backward);
+}
+BRO_HD uint32_t score_last_distance(int hash_type, uint32_t len, uint32_t i) {
+  if (hash_type == 9) {
+    const uint16_t cost[16] = {7740, 7585, 7563, 7553, 7587, 7587, 7584, 7584, 7581, 7581, 7575, 7575, 7565, 7565, 7555, 7555};
+    return (540u * len + cost[i]) >> 2;
+  }
+  uint32_t s = 135u * len + 1935u;
+  if (i != 0) s -= 39u + ((0x1ca10u >> (i & 0xe)) & 0xe);
+  return s;
+}
+#define BRO_MIN_SCORE 2020u
+
+// hash key of the bytes at p (buffer must be readable 8 bytes past p)
+BRO_HD uint32_t load32(const uint8_t* p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+BRO_HD uint32_t hash_key_from_words(int hash_type, int key_bits, uint32_t lo, uint32_t hi) {
+  if (hash_type == 6) {  // 5 bytes: mod.rs:1138-1140, encode.rs:1066-1067
+    uint64_t v = ((uint64_t)(hi & 0xFFu) << 32) | lo;
+    return (uint32_t)((v * 0x1fe35a7bd3579bd3ull) >> (64 - key_bits));
+  }
+  return (uint32_t)(lo * 0x1e35a7bdu) >> (32 - key_bits);  // mod.rs:990-991, :734-738
+}
+BRO_HD uint32_t hash_key(int hash_type, int key_bits, const uint8_t* p) {
+  return hash_key_from_words(hash_type, key_bits, load32(p), (uint32_t)p[4]);
+}
+
+BRO_HD uint32_t lcp_bytes(const uint8_t* a, const uint8_t* b, uint32_t max_len) {
+  uint32_t i = 0;
+  while (i < max_len && a[i] == b[i]) ++i;
+  return i;
+}
+
+struct Match {
+  uint32_t len, dist, score;
+};
+
+// candidate i of the (expanded) distance cache: mod.rs:632-655
+BRO_HD int32_t cache_candidate(const int32_t* dc, int i) {
+  const int8_t idx[16] = {0, 1, 2, 3, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1};
+  const int8_t off[16] = {0, 0, 0, 0, -1, 1, -2, 2, -3, 3, -1, 1, -2, 2, -3, 3};
+  return dc[idx[i]] + off[i];
+}
+
+// Best match at pos: last-distance probes (serial state) combined with the precomputed bucket candidate.
+BRO_HD_NOINLINE bool find_match(const EncParams& P, const uint8_t* data, const uint32_t* best, const int32_t* dc,
+                                uint32_t pos, uint32_t max_len, Match* out) {
+  const uint32_t max_backward = bmin(pos, P.max_backward);
+  uint32_t best_score = BRO_MIN_SCORE, best_len = 0, best_dist = 0;
+  bool found = false;
+  const uint8_t* cur = data + pos;
+  for (int i = 0; i < P.n_last; ++i) {
+    int32_t back = cache_candidate(dc, i);
+    if (back <= 0 || (uint32_t)back > max_backward) continue;
+    const uint8_t* prev = cur - back;
+    if (best_len < max_len && cur[best_len] != prev[best_len]) continue;
+    uint32_t len = lcp_bytes(prev, cur, max_len);
+    if (len >= 3 || (len == 2 && i < 2)) {
+      uint32_t score = score_last_distance(P.hash_type, len, (uint32_t)i);
+      if (best_score < score) {
+        best_score = score; best_len = len; best_dist = (uint32_t)back;
+        found = true;
+      }
+    }
+  }
+  uint32_t b = best[pos];
+  uint32_t blen = b & 0xFFu;
+  if (blen != 0) {
+    uint32_t bdist = b >> 8;
+    uint32_t len = bmin(blen, max_len);
+    if (blen >= P.lcap && max_len > len) len += lcp_bytes(cur - bdist + len, cur + len, max_len - len);
+    if (len >= 4) {
+      uint32_t score = score_regular(P.hash_type, len, bdist);
+      if (best_score < score) {
+        best_score = score; best_len = len; best_dist = bdist;
+        found = true;
+      }
+    }
+  }
+  out->len = best_len; out->dist = best_dist; out->score = best_score;
+  return found;
+}
+
+// Greedy + lazy parse of [ustart, uend).  Writes commands (copy_len >= 2) to out[], returns their number;
+// *tail = literals after the last copy, *ncopy = total bytes covered by copies.
+BRO_HD_NOINLINE uint32_t parse_unit(const EncParams& P, const uint8_t* data, const uint32_t* best, uint32_t ustart,
+                                    uint32_t uend, RawCmd* out, uint32_t* tail, uint32_t* ncopy) {
+  int32_t dc[4] = {0x3fffffff, 0x3fffffff, 0x3fffffff, 0x3fffffff};  // unit-local cache starts unknown
+  const uint32_t hash_type_len = P.hash_type == 6 ? 8u : 4u;
+  const uint32_t window = P.quality < 9 ? 64u : 512u;
+  uint32_t pos = ustart, insert_len = 0, ncmd = 0, copied = 0;
+  uint32_t apply_random_heuristics = pos + window;
+  while (pos + hash_type_len < uend) {
+    uint32_t max_len = uend - pos;
+    Match m;
+    if (find_match(P, data, best, dc, pos, max_len, &m)) {
+      int delayed = 0;
+      max_len--;
+      for (;; max_len--) {
+        Match m2;
+        bool f2 = find_match(P, data, best, dc, pos + 1, max_len, &m2);
+        if (f2 && m2.score >= m.score + 175u) {
+          pos++;
+          insert_len++;
+          m = m2;
+          if (++delayed < 4 && pos + hash_type_len < uend) continue;
+        }
+        break;
+      }
+      apply_random_heuristics = pos + 2 * m.len + window;
+      if ((int32_t)m.dist != dc[0]) {
+        dc[3] = dc[2]; dc[2] = dc[1]; dc[1] = dc[0]; dc[0] = (int32_t)m.dist;
+      }
+      out[ncmd].insert_len = insert_len;
+      out[ncmd].copy_len = m.len;
+      out[ncmd].distance = m.dist;
+      ++ncmd;
+      insert_len = 0;
+      copied += m.len;
+      pos += m.len;
+    } else {
+      insert_len++;
+      pos++;
+      if (pos > apply_random_heuristics) {
+        const uint32_t margin = bmax(hash_type_len - 1u, 4u);
+        if (pos + 16 + margin >= uend) {
+          insert_len += uend - pos;
+          pos = uend;
+        } else if (pos > apply_random_heuristics + 4 * window) {
+          insert_len += 16;
+          pos += 16;
+        } else {
+          insert_len += 8;
+          pos += 8;
+        }
+      }
+    }
+  }
+  insert_len += uend - pos;
+  *tail = insert_len;
+  *ncopy = copied;
+  return ncmd;
+}
+
+}  // namespace bro
