@@ -1,0 +1,328 @@
+// bro_capi.cu -- the reference's C ABI (src/ffi/compressor.rs, src/ffi/multicompress/mod.rs) on top of the device
+// encoder.  Host-side state machine only; every byte of compressed output is produced by the CUDA path.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "brotli_b200.h"
+#include "bro_encoder.h"
+
+namespace {
+
+struct EncoderParams {  // the subset of BrotliEncoderParams (backward_references/mod.rs:71-125) this path consumes
+  int quality = 11;     // defaults: encode.rs:318-357
+  int lgwin = 22;
+  int mode = 0;
+  uint64_t size_hint = 0;
+  int disable_ctx = 0;
+  int catable = 0, appendable = 0, magic_number = 0, byte_align = 0, bare_stream = 0;
+};
+
+bool apply_param(EncoderParams& p, int key, uint32_t value) {
+  switch (key) {
+    case BROTLI_PARAM_MODE: p.mode = (int)value; return true;
+    case BROTLI_PARAM_QUALITY: p.quality = (int)value; return true;
+    case BROTLI_PARAM_LGWIN: p.lgwin = (int)value; return true;
+    case BROTLI_PARAM_LGBLOCK: return true;  // parse granularity is a device-side constant here
+    case BROTLI_PARAM_DISABLE_LITERAL_CONTEXT_MODELING: p.disable_ctx = (int)value; return true;
+    case BROTLI_PARAM_SIZE_HINT: p.size_hint = value; return true;
+    case BROTLI_PARAM_LARGE_WINDOW: return true;  // windows above 2^24 are clamped (SanitizeParams encode.rs:546-558)
+    case BROTLI_PARAM_CATABLE: p.catable = value != 0; if (p.catable) p.appendable = 1; return true;
+    case BROTLI_PARAM_APPENDABLE: p.appendable = value != 0; return true;
+    case BROTLI_PARAM_MAGIC_NUMBER: p.magic_number = value != 0; return true;
+    case BROTLI_PARAM_BYTE_ALIGN: p.byte_align = value != 0; return true;
+    case BROTLI_PARAM_BARE_STREAM: p.bare_stream = value != 0; if (p.bare_stream) p.byte_align = 1; return true;
+    default:
+      // research / divans knobs of the reference (stride, prior, cdf speeds ...) have no effect on this path
+      return key >= 150 && key <= 173;
+  }
+}
+
+// one lazily created encoder per device for the state-less entry points
+std::mutex g_mu;
+std::vector<B200Encoder*> g_encoders;
+std::vector<std::mutex*> g_encoder_mu;
+
+B200Encoder* shared_encoder(int device, std::mutex** mu) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int n = b200_device_count();
+  if (n <= 0 || device >= n) return nullptr;
+  if ((int)g_encoders.size() < n) {
+    g_encoders.resize(n, nullptr);
+    g_encoder_mu.resize(n, nullptr);
+  }
+  if (!g_encoders[device]) {
+    g_encoders[device] = b200_encoder_create(device);
+    g_encoder_mu[device] = new std::mutex();
+  }
+  *mu = g_encoder_mu[device];
+  return g_encoders[device];
+}
+
+}  // namespace
+
+struct BrotliEncoderStateStruct {
+  EncoderParams params;
+  B200Encoder* enc = nullptr;
+  std::vector<uint8_t> input;   // everything consumed so far (the device sees it as the match window)
+  size_t flushed = 0;           // bytes of `input` already turned into output
+  std::vector<uint8_t> output;  // produced, not yet taken
+  size_t out_pos = 0;
+  bool started = false, finished = false, header_written = false;
+};
+
+struct BrotliEncoderWorkPoolStruct {
+  size_t num_workers;
+  std::vector<B200Encoder*> encoders;  // one per visible GPU
+};
+
+extern "C" {
+
+uint32_t BrotliEncoderVersion(void) { return 0x08000004u; /* tracks crate 8.0.4 */ }
+
+size_t BrotliEncoderMaxCompressedSize(size_t input_size) {  // encode.rs:1273-1299
+  size_t num_large_blocks = input_size >> 14;
+  size_t tail = input_size - (num_large_blocks << 24);
+  (void)tail;
+  size_t overhead = 2 + 4 * (input_size >> 24) + 3 + 1;
+  size_t result = input_size + overhead + (input_size >> 10) * 8 + 4096;
+  if (input_size == 0) return 2;
+  return result < input_size ? 0 : result;
+}
+size_t BrotliEncoderMaxCompressedSizeMulti(size_t input_size, size_t num_threads) {  // multicompress/mod.rs:49
+  return BrotliEncoderMaxCompressedSize(input_size) + num_threads * 8;
+}
+
+BrotliEncoderState* BrotliEncoderCreateInstance(brotli_alloc_func alloc_func, brotli_free_func free_func, void* opaque) {
+  (void)free_func;
+  if (alloc_func) {  // honour "allocator returns NULL => NULL instance" (compressor.rs:97-99, :452-473)
+    void* probe = alloc_func(opaque, sizeof(BrotliEncoderStateStruct));
+    if (!probe) return nullptr;
+    if (free_func) free_func(opaque, probe);
+  }
+  B200Encoder* enc = b200_encoder_create(0);
+  if (!enc) return nullptr;
+  BrotliEncoderStateStruct* s = new (std::nothrow) BrotliEncoderStateStruct();
+  if (!s) { b200_encoder_destroy(enc); return nullptr; }
+  s->enc = enc;
+  return s;
+}
+void BrotliEncoderDestroyInstance(BrotliEncoderState* s) {
+  if (!s) return;
+  b200_encoder_destroy(s->enc);
+  delete s;
+}
+BROTLI_BOOL BrotliEncoderSetParameter(BrotliEncoderState* s, BrotliEncoderParameter p, uint32_t value) {
+  if (!s || s->started) return BROTLI_FALSE;  // encode.rs:289-295
+  return apply_param(s->params, (int)p, value) ? BROTLI_TRUE : BROTLI_FALSE;
+}
+
+static bool state_emit(BrotliEncoderStateStruct* s, bool last) {
+  const size_t start = s->flushed, len = s->input.size() - start;
+  const bool first = !s->header_written;
+  if (len == 0) {
+    if (last) {
+      if (first) s->output.push_back(6);        // empty stream, encode.rs:1463
+      else s->output.push_back(3);              // ISLAST + ISLASTEMPTY after a byte-aligned flush
+      s->header_written = true;
+    }
+    return true;
+  }
+  size_t cap = b200_max_compressed_size(len) + 16, got = 0;
+  size_t old = s->output.size();
+  s->output.resize(old + cap);
+  b200_encoder_set_option(s->enc, B200_OPT_CTX_MODEL, s->params.disable_ctx ? 0 : 1);
+  uint64_t hint = s->params.size_hint ? s->params.size_hint : s->input.size();
+  int ok = b200_encoder_compress_range(s->enc, s->params.quality, s->params.lgwin, hint, s->input.data(), s->input.size(), start, len,
+                                       first ? 1 : 0, last ? 1 : 0, last ? 0 : 1, s->output.data() + old, cap, &got, 0);
+  if (!ok) { s->output.resize(old); return false; }
+  s->output.resize(old + got);
+  s->flushed = s->input.size();
+  s->header_written = true;
+  return true;
+}
+
+BROTLI_BOOL BrotliEncoderCompressStream(BrotliEncoderState* s, BrotliEncoderOperation op, size_t* available_in,
+                                        const uint8_t** next_in, size_t* available_out, uint8_t** next_out, size_t* total_out) {
+  if (!s || !available_in || !available_out) return BROTLI_FALSE;
+  if (op == BROTLI_OPERATION_EMIT_METADATA) return BROTLI_FALSE;  // not on this path
+  if (*available_in) {
+    if (s->finished) return BROTLI_FALSE;
+    s->started = true;
+    s->input.insert(s->input.end(), *next_in, *next_in + *available_in);
+    *next_in += *available_in;
+    *available_in = 0;
+  }
+  if (op == BROTLI_OPERATION_FLUSH && s->flushed < s->input.size()) {
+    if (!state_emit(s, false)) return BROTLI_FALSE;
+  } else if (op == BROTLI_OPERATION_FINISH && !s->finished) {
+    s->started = true;
+    if (!state_emit(s, true)) return BROTLI_FALSE;
+    s->finished = true;
+  }
+  size_t avail = s->output.size() - s->out_pos;
+  if (avail && *available_out && next_out && *next_out) {
+    size_t n = std::min(avail, *available_out);
+    memcpy(*next_out, s->output.data() + s->out_pos, n);
+    *next_out += n;
+    *available_out -= n;
+    s->out_pos += n;
+    if (total_out) *total_out += n;
+  }
+  if (s->out_pos == s->output.size()) { s->output.clear(); s->out_pos = 0; }
+  return BROTLI_TRUE;
+}
+BROTLI_BOOL BrotliEncoderIsFinished(BrotliEncoderState* s) { return (s && s->finished && s->out_pos == s->output.size()) ? 1 : 0; }
+BROTLI_BOOL BrotliEncoderHasMoreOutput(BrotliEncoderState* s) { return (s && s->out_pos < s->output.size()) ? 1 : 0; }
+const uint8_t* BrotliEncoderTakeOutput(BrotliEncoderState* s, size_t* size) {  // encode.rs:3006-3027
+  if (!s || !size) return nullptr;
+  size_t avail = s->output.size() - s->out_pos;
+  size_t n = *size ? std::min(*size, avail) : avail;
+  if (n == 0) { *size = 0; return nullptr; }
+  const uint8_t* p = s->output.data() + s->out_pos;
+  s->out_pos += n;
+  *size = n;
+  return p;
+}
+
+BROTLI_BOOL BrotliEncoderCompress(int quality, int lgwin, BrotliEncoderMode mode, size_t input_size, const uint8_t* input,
+                                  size_t* encoded_size, uint8_t* encoded) {
+  (void)mode;
+  if (!encoded_size || *encoded_size == 0) return BROTLI_FALSE;  // encode.rs:1459-1462
+  const size_t out_cap = *encoded_size;
+  if (input_size == 0) { encoded[0] = 6; *encoded_size = 1; return BROTLI_TRUE; }
+  std::mutex* mu = nullptr;
+  B200Encoder* enc = shared_encoder(0, &mu);
+  if (!enc) { *encoded_size = 0; return BROTLI_FALSE; }
+  size_t got = 0;
+  int ok;
+  {
+    std::lock_guard<std::mutex> lk(*mu);
+    b200_encoder_set_option(enc, B200_OPT_CTX_MODEL, 1);
+    ok = b200_encoder_compress(enc, quality, lgwin, input, input_size, encoded, out_cap, &got, 0);
+  }
+  if (!ok) {  // no CPU-produced stream, ever: a device failure (or a too-small output buffer) is reported as failure
+    *encoded_size = 0;
+    return BROTLI_FALSE;
+  }
+  *encoded_size = got;
+  return BROTLI_TRUE;
+}
+
+// ---- multi ----
+static int32_t compress_multi_impl(const std::vector<B200Encoder*>& encs, std::vector<std::mutex*>* mus, size_t num_params,
+                                   const BrotliEncoderParameter* keys, const uint32_t* values, size_t input_size,
+                                   const uint8_t* input, size_t* encoded_size, uint8_t* encoded, size_t desired_num_threads) {
+  if (!encoded_size || encs.empty()) return 0;
+  EncoderParams p;
+  for (size_t i = 0; i < num_params; ++i) apply_param(p, (int)keys[i], values[i]);
+  size_t shards = std::max<size_t>(1, std::min<size_t>(desired_num_threads, 16));  // MAX_THREADS, fixed_queue.rs:1
+  if (input_size == 0) {
+    if (*encoded_size < 1) return 0;
+    encoded[0] = 6;
+    *encoded_size = 1;
+    return 1;
+  }
+  if (shards > input_size) shards = input_size;
+  std::vector<std::vector<uint8_t>> outs(shards);
+  std::vector<int> oks(shards, 0);
+  const size_t ngpu = encs.size();
+  auto work = [&](size_t g) {  // one host thread per GPU walks its shards in order
+    for (size_t i = g; i < shards; i += ngpu) {
+      size_t a = i * input_size / shards, b = (i + 1) * input_size / shards;  // get_range threading/mod.rs:333
+      size_t cap = b200_max_compressed_size(b - a) + 16, got = 0;
+      outs[i].resize(cap);
+      std::unique_lock<std::mutex> lk;
+      if (mus) lk = std::unique_lock<std::mutex>(*(*mus)[g]);
+      // compress_part threading/mod.rs:337-383: size_hint = shard length
+      uint64_t hint = p.size_hint ? p.size_hint : (b - a);
+      b200_encoder_set_option(encs[g], B200_OPT_CTX_MODEL, p.disable_ctx ? 0 : 1);
+      oks[i] = b200_encoder_compress_range(encs[g], p.quality, p.lgwin, hint, input, input_size, a, b - a, i == 0 ? 1 : 0,
+                                           i + 1 == shards ? 1 : 0, i + 1 == shards ? 0 : 1, outs[i].data(), cap, &got, 0);
+      outs[i].resize(oks[i] ? got : 0);
+    }
+  };
+  std::vector<std::thread> th;
+  for (size_t g = 1; g < std::min(ngpu, shards); ++g) th.emplace_back(work, g);
+  work(0);
+  for (auto& t : th) t.join();  // always join every worker, first error wins (threading/mod.rs:565-660)
+  size_t total = 0;
+  for (size_t i = 0; i < shards; ++i) {
+    if (!oks[i]) return 0;
+    total += outs[i].size();
+  }
+  if (total > *encoded_size) return 0;  // BrotliEncoderThreadError::InsufficientOutputSpace
+  size_t off = 0;
+  for (size_t i = 0; i < shards; ++i) {  // shards end byte aligned: concatenation is a plain copy
+    memcpy(encoded + off, outs[i].data(), outs[i].size());
+    off += outs[i].size();
+  }
+  *encoded_size = total;
+  return 1;
+}
+
+int32_t BrotliEncoderCompressMulti(size_t num_params, const BrotliEncoderParameter* keys, const uint32_t* values, size_t input_size,
+                                   const uint8_t* input, size_t* encoded_size, uint8_t* encoded, size_t desired_num_threads,
+                                   brotli_alloc_func alloc_func, brotli_free_func free_func, void** alloc_opaque_per_thread) {
+  (void)alloc_func; (void)free_func; (void)alloc_opaque_per_thread;
+  int n = b200_device_count();
+  if (n <= 0) return 0;
+  std::vector<B200Encoder*> encs;
+  std::vector<std::mutex*> mus;
+  for (int d = 0; d < n; ++d) {
+    std::mutex* mu = nullptr;
+    B200Encoder* e = shared_encoder(d, &mu);
+    if (!e) return 0;
+    encs.push_back(e);
+    mus.push_back(mu);
+  }
+  return compress_multi_impl(encs, &mus, num_params, keys, values, input_size, input, encoded_size, encoded, desired_num_threads);
+}
+
+BrotliEncoderWorkPool* BrotliEncoderCreateWorkPool(size_t num_workers, brotli_alloc_func alloc_func, brotli_free_func free_func,
+                                                   void** alloc_opaque_per_thread) {
+  if (alloc_func) {  // NULL-returning allocator => NULL pool (multicompress/test.rs)
+    void* probe = alloc_func(alloc_opaque_per_thread ? alloc_opaque_per_thread[0] : nullptr, 64);
+    if (!probe) return nullptr;
+    if (free_func) free_func(alloc_opaque_per_thread ? alloc_opaque_per_thread[0] : nullptr, probe);
+  }
+  int n = b200_device_count();
+  if (n <= 0) return nullptr;
+  BrotliEncoderWorkPoolStruct* pool = new (std::nothrow) BrotliEncoderWorkPoolStruct();
+  if (!pool) return nullptr;
+  pool->num_workers = num_workers;
+  size_t want = std::max<size_t>(1, std::min<size_t>(num_workers ? num_workers : 1, (size_t)n));
+  for (size_t d = 0; d < want; ++d) {
+    B200Encoder* e = b200_encoder_create((int)d);
+    if (!e) {
+      for (auto* x : pool->encoders) b200_encoder_destroy(x);
+      delete pool;
+      return nullptr;
+    }
+    pool->encoders.push_back(e);
+  }
+  return pool;
+}
+void BrotliEncoderDestroyWorkPool(BrotliEncoderWorkPool* pool) {
+  if (!pool) return;
+  for (auto* e : pool->encoders) b200_encoder_destroy(e);
+  delete pool;
+}
+int32_t BrotliEncoderCompressWorkPool(BrotliEncoderWorkPool* pool, size_t num_params, const BrotliEncoderParameter* keys,
+                                      const uint32_t* values, size_t input_size, const uint8_t* input, size_t* encoded_size,
+                                      uint8_t* encoded, size_t desired_num_threads, brotli_alloc_func alloc_func,
+                                      brotli_free_func free_func, void** alloc_opaque_per_thread) {
+  (void)alloc_func; (void)free_func; (void)alloc_opaque_per_thread;
+  if (!pool) return BrotliEncoderCompressMulti(num_params, keys, values, input_size, input, encoded_size, encoded,
+                                               desired_num_threads, nullptr, nullptr, nullptr);
+  return compress_multi_impl(pool->encoders, nullptr, num_params, keys, values, input_size, input, encoded_size, encoded,
+                             desired_num_threads);
+}
+
+}  // extern "C"

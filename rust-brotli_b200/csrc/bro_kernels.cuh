@@ -1,0 +1,910 @@
+// bro_kernels.cuh -- CUDA kernels (sm_100a) of the brotli compression hot path.
+//
+// Stage map (DESIGN.md has the data layout and the per-kernel roofline):
+//   sort    k_sort_hist / k_scan_rows / k_scan_digits / k_sort_scatter   stable LSD radix sort of positions by
+//                                                                        bucket key  (replaces hasher Store*)
+//   match   k_match          every position vs the `depth` most recent earlier positions of its bucket
+//                            (replaces the bucket walk of FindLongestMatch, backward_references/mod.rs:1754-1792)
+//   parse   k_parse          greedy+lazy parse per unit (CreateBackwardReferences mod.rs:2376)
+//   final   k_fin_count / k_fin_write / k_fin_dist    command records, literal/distance ranks
+//   ctx     k_ctx_decide     literal context map choice (encode.rs:1873)
+//   syms    k_symbols        symbol streams for the splitter
+//   split   k_split_simple / k_split_greedy           histograms + greedy block split (metablock.rs:551-1021)
+//   header  k_header         Huffman codes + metablock header bits (brotli_bit_stream.rs:2035-2190)
+//   emit    k_bitlen / k_bitscan / k_layout / k_emit_header / k_emit_body / k_emit_raw
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bro_common.cuh"
+#include "bro_finalize.cuh"
+#include "bro_huffman.cuh"
+#include "bro_meta.cuh"
+#include "bro_parse.cuh"
+#include "bro_split.cuh"
+
+namespace bro {
+
+// ---------------------------------------------------------------------------------------------------
+// device-side descriptors
+// ---------------------------------------------------------------------------------------------------
+struct MBDesc {
+  uint32_t start, len;        // input span
+  uint32_t u0, u1;            // parse units
+  uint32_t ncmd, nlit, ndist; // symbol counts
+  int ctx_map_id;
+  uint32_t hdr_bits;
+  uint32_t raw;               // stored uncompressed
+  uint64_t body_bits;
+  uint64_t out_bitpos;        // position of the metablock in the output stream
+};
+
+struct SplitArrays {  // per metablock, per category
+  uint8_t* types;
+  uint32_t* lengths;
+  uint32_t* starts;
+  uint32_t* num_blocks;   // [1]
+  uint32_t* num_types;    // [1]
+  uint32_t* histograms;   // [(max_types + 1)][nctx * A]
+  SplitCode* sc;
+};
+
+struct Workspace {
+  // input
+  const uint8_t* data;  // padded with >= 320 zero bytes
+  const uint32_t* lut;
+  EncParams P;
+  uint32_t num_units, num_mb;
+  // match
+  uint32_t* best;
+  // parse
+  RawCmd* raw;
+  uint32_t *unit_ncmd, *unit_tail, *unit_ncopy;
+  uint32_t *unit_cmd_off, *unit_lit_off, *unit_ndist;  // metablock-relative
+  // commands
+  GCmd* cmds;           // [num_mb][cmd_cap]
+  uint32_t cmd_cap;     // per metablock
+  uint32_t* cmd_bits;   // [num_mb][cmd_cap] bit length, then exclusive prefix
+  // symbol streams
+  uint16_t* lit_syms;   // [n]  literal | ctx << 8, metablock m at m.start
+  uint16_t* cmd_syms;   // [num_mb][cmd_cap]
+  uint16_t* dist_syms;  // [num_mb][cmd_cap]
+  // metablocks
+  MBDesc* mb;
+  // splits: capacities per metablock
+  uint32_t lit_blk_cap, cmd_blk_cap, dist_blk_cap;
+  uint32_t max_lit_trees, max_cmd_types, max_dist_types;
+  uint8_t *lit_types, *cmd_types, *dist_types;
+  uint32_t *lit_lengths, *cmd_lengths, *dist_lengths;
+  uint32_t *lit_starts, *cmd_starts, *dist_starts;
+  uint32_t* split_counts;  // [num_mb][6]: lit nb, lit nt, cmd nb, cmd nt, dist nb, dist nt
+  uint32_t *lit_hist, *cmd_hist, *dist_hist;
+  SplitCode* split_codes;  // [num_mb][3]
+  // codes
+  uint8_t *lit_depth, *cmd_depth, *dist_depth;
+  uint16_t *lit_code, *cmd_code, *dist_code;
+  // header
+  uint8_t* hdr;           // [num_mb][hdr_cap]
+  uint32_t hdr_cap;
+  HuffStoreWs* huff_ws;   // [num_mb]
+  uint32_t* ctxmap_ws;    // [num_mb][max_lit_types * 64]
+  // output
+  uint32_t* out;          // zero-initialised words
+  uint64_t out_cap_bytes;
+  uint64_t* total_bits;   // [1]
+};
+
+__device__ __forceinline__ SplitView make_view(const Workspace& W, uint32_t m, int cat) {
+  SplitView v;
+  const uint32_t* cnt = W.split_counts + (size_t)m * 6;
+  if (cat == 0) {
+    v.types = W.lit_types + (size_t)m * W.lit_blk_cap; v.lengths = W.lit_lengths + (size_t)m * W.lit_blk_cap;
+    v.starts = W.lit_starts + (size_t)m * W.lit_blk_cap; v.num_blocks = cnt[0]; v.num_types = cnt[1];
+  } else if (cat == 1) {
+    v.types = W.cmd_types + (size_t)m * W.cmd_blk_cap; v.lengths = W.cmd_lengths + (size_t)m * W.cmd_blk_cap;
+    v.starts = W.cmd_starts + (size_t)m * W.cmd_blk_cap; v.num_blocks = cnt[2]; v.num_types = cnt[3];
+  } else {
+    v.types = W.dist_types + (size_t)m * W.dist_blk_cap; v.lengths = W.dist_lengths + (size_t)m * W.dist_blk_cap;
+    v.starts = W.dist_starts + (size_t)m * W.dist_blk_cap; v.num_blocks = cnt[4]; v.num_types = cnt[5];
+  }
+  return v;
+}
+__device__ __forceinline__ MetaCodes make_codes(const Workspace& W, uint32_t m) {
+  MetaCodes mc;
+  mc.lit = make_view(W, m, 0); mc.cmd = make_view(W, m, 1); mc.dist = make_view(W, m, 2);
+  mc.lit_sc = W.split_codes + (size_t)m * 3; mc.cmd_sc = mc.lit_sc + 1; mc.dist_sc = mc.lit_sc + 2;
+  mc.lit_depth = W.lit_depth + (size_t)m * W.max_lit_trees * 256; mc.lit_code = W.lit_code + (size_t)m * W.max_lit_trees * 256;
+  mc.cmd_depth = W.cmd_depth + (size_t)m * W.max_cmd_types * 704; mc.cmd_code = W.cmd_code + (size_t)m * W.max_cmd_types * 704;
+  mc.dist_depth = W.dist_depth + (size_t)m * W.max_dist_types * 64; mc.dist_code = W.dist_code + (size_t)m * W.max_dist_types * 64;
+  mc.ctx_map_id = W.mb[m].ctx_map_id;
+  mc.nctx = ctxmap_num_contexts(mc.ctx_map_id);
+  return mc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Radix sort of the positions of one batch by bucket key (stable => ascending position inside a bucket).
+// Pass 0 sorts by key & 0xFF reading the input bytes; pass 1 by key >> 8 reading the packed words of pass 0.
+// Element word: (key >> 8) << 25 | (position - batch_origin).
+// ---------------------------------------------------------------------------------------------------
+#define SORT_THREADS 256
+#define SORT_ITEMS 16
+#define SORT_TILE (SORT_THREADS * SORT_ITEMS)
+
+struct SortArgs {
+  const uint8_t* data;   // data + batch_origin
+  uint32_t count;        // positions in batch (halo + payload)
+  const uint32_t* in;    // pass 1 input
+  uint32_t* outw;        // pass output
+  uint32_t* hist;        // [256][num_tiles]
+  const uint32_t* digit_base;  // [256]
+  uint32_t num_tiles;
+  int hash_type, key_bits;
+  int pass;
+};
+
+__device__ __forceinline__ uint32_t smem_key(const uint32_t* sw, uint32_t e, int hash_type, int key_bits) {
+  // bytes e..e+7 of the tile staged as little-endian words
+  uint32_t w0 = sw[e >> 2], w1 = sw[(e >> 2) + 1], w2 = sw[(e >> 2) + 2];
+  uint32_t sh = (e & 3u) * 8u;
+  uint32_t lo = __funnelshift_r(w0, w1, sh);
+  uint32_t hi = __funnelshift_r(w1, w2, sh);
+  return hash_key_from_words(hash_type, key_bits, lo, hi);
+}
+
+__device__ __forceinline__ void sort_stage_tile(const SortArgs& a, uint32_t tile, uint32_t* sw) {
+  // stage SORT_TILE + 8 bytes (input is padded, so reading past `count` is safe)
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(a.data) + (size_t)tile * (SORT_TILE / 4);
+  for (uint32_t i = threadIdx.x; i < SORT_TILE / 4 + 4; i += SORT_THREADS) sw[i] = src[i];
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(SortArgs a) {
+  __shared__ uint32_t sw[SORT_TILE / 4 + 4];
+  __shared__ uint32_t sh[256];
+  const uint32_t tile = blockIdx.x;
+  sh[threadIdx.x] = 0;
+  if (a.pass == 0) sort_stage_tile(a, tile, sw);
+  __syncthreads();
+  const uint32_t base = tile * SORT_TILE;
+#pragma unroll 4
+  for (int r = 0; r < SORT_ITEMS; ++r) {
+    uint32_t e = r * SORT_THREADS + threadIdx.x;
+    if (base + e < a.count) {
+      uint32_t digit;
+      if (a.pass == 0) digit = smem_key(sw, e, a.hash_type, a.key_bits) & 0xFFu;
+      else digit = a.in[base + e] >> 25;
+      atomicAdd(&sh[digit], 1u);
+    }
+  }
+  __syncthreads();
+  a.hist[(size_t)threadIdx.x * a.num_tiles + tile] = sh[threadIdx.x];
+}
+
+// exclusive scan of each digit row over tiles; row totals to totals[digit]
+__global__ void __launch_bounds__(256) k_scan_rows(uint32_t* hist, uint32_t num_tiles, uint32_t* totals) {
+  __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_carry;
+  uint32_t* row = hist + (size_t)blockIdx.x * num_tiles;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < num_tiles; base += 256) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < num_tiles ? row[i] : 0;
+    uint32_t x = v;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= (uint32_t)o) x += y;
+    }
+    if (lane == 31) s_warp[wid] = x;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (uint32_t w = 0; w < wid; ++w) woff += s_warp[w];
+    uint32_t carry = s_carry;
+    if (i < num_tiles) row[i] = carry + woff + x - v;
+    __syncthreads();
+    if (threadIdx.x == 255) s_carry = carry + woff + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) totals[blockIdx.x] = s_carry;
+}
+__global__ void __launch_bounds__(256) k_scan_digits(const uint32_t* totals, uint32_t* digit_base) {
+  __shared__ uint32_t s[256];
+  s[threadIdx.x] = totals[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0;
+    for (int i = 0; i < 256; ++i) { uint32_t v = s[i]; s[i] = acc; acc += v; }
+  }
+  __syncthreads();
+  digit_base[threadIdx.x] = s[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(SortArgs a) {
+  __shared__ uint32_t sw[SORT_TILE / 4 + 4];
+  __shared__ uint32_t wc[SORT_THREADS / 32][256];
+  const uint32_t tile = blockIdx.x;
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (uint32_t i = threadIdx.x; i < (SORT_THREADS / 32) * 256; i += SORT_THREADS) (&wc[0][0])[i] = 0;
+  if (a.pass == 0) sort_stage_tile(a, tile, sw);
+  __syncthreads();
+  const uint32_t base = tile * SORT_TILE;
+  uint32_t word[SORT_ITEMS];
+  uint16_t lrank[SORT_ITEMS];
+  uint8_t dig[SORT_ITEMS];
+  // element order inside the tile: warp-major, then round, then lane  (=> ascending position)
+#pragma unroll
+  for (int r = 0; r < SORT_ITEMS; ++r) {
+    uint32_t e = wid * (32 * SORT_ITEMS) + r * 32 + lane;
+    bool valid = base + e < a.count;
+    uint32_t digit = 0x100u, w = 0;
+    if (valid) {
+      if (a.pass == 0) {
+        uint32_t key = smem_key(sw, e, a.hash_type, a.key_bits);
+        digit = key & 0xFFu;
+        w = ((key >> 8) << 25) | (base + e);
+      } else {
+        uint32_t v = a.in[base + e];
+        digit = v >> 25;
+        w = v & 0x1FFFFFFu;
+      }
+    }
+    uint32_t peers = __match_any_sync(0xffffffffu, digit);
+    uint32_t rank_in_round = __popc(peers & ((1u << lane) - 1u));
+    uint32_t old = 0;
+    if (valid) old = wc[wid][digit];
+    __syncwarp();
+    if (valid && rank_in_round == 0) wc[wid][digit] = old + __popc(peers);
+    __syncwarp();
+    word[r] = w;
+    dig[r] = (uint8_t)digit;
+    lrank[r] = (uint16_t)(old + rank_in_round);
+    if (!valid) dig[r] = 0, lrank[r] = 0xFFFF;
+  }
+  __syncthreads();
+  {  // per digit: exclusive scan over warps, seeded with the global offset of (digit, tile)
+    uint32_t d = threadIdx.x;
+    uint32_t acc = a.digit_base[d] + a.hist[(size_t)d * a.num_tiles + tile];
+    for (int w = 0; w < SORT_THREADS / 32; ++w) {
+      uint32_t t = wc[w][d];
+      wc[w][d] = acc;
+      acc += t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < SORT_ITEMS; ++r) {
+    if (lrank[r] != 0xFFFF) a.outw[wc[wid][dig[r]] + lrank[r]] = word[r];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Match search over the sorted position list of one batch.
+// ---------------------------------------------------------------------------------------------------
+#define MATCH_THREADS 256
+
+struct MatchArgs {
+  const uint8_t* data;      // whole input (padded)
+  const uint32_t* sorted;   // [count] batch-relative positions sorted by (key, position)
+  uint32_t count;
+  uint32_t origin;          // absolute position of batch-relative 0
+  uint32_t payload_begin;   // batch-relative first position whose match is wanted
+  uint32_t n;               // input size
+  uint32_t* best;
+  int hash_type, key_bits, depth;
+  uint32_t lcap, max_backward;
+};
+
+__device__ __forceinline__ void load16_unaligned(const uint8_t* p, uint32_t* w) {
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+  uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
+  uint32_t a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2), a3 = __ldg(q + 3), a4 = __ldg(q + 4);
+  w[0] = __funnelshift_r(a0, a1, sh);
+  w[1] = __funnelshift_r(a1, a2, sh);
+  w[2] = __funnelshift_r(a2, a3, sh);
+  w[3] = __funnelshift_r(a3, a4, sh);
+}
+
+// dynamic shared memory: (MATCH_THREADS + depth) entries x 6 words
+__global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
+  extern __shared__ uint32_t smem[];
+  const uint32_t E = MATCH_THREADS + (uint32_t)a.depth;
+  uint32_t* s_pos = smem;
+  uint32_t* s_key = smem + E;
+  uint32_t* s_d0 = smem + 2 * E;
+  uint32_t* s_d1 = smem + 3 * E;
+  uint32_t* s_d2 = smem + 4 * E;
+  uint32_t* s_d3 = smem + 5 * E;
+  const int64_t j0 = (int64_t)blockIdx.x * MATCH_THREADS - a.depth;  // sorted index of smem entry 0
+  for (uint32_t i = threadIdx.x; i < E; i += MATCH_THREADS) {
+    int64_t j = j0 + i;
+    uint32_t pos = 0xFFFFFFFFu, key = 0xFFFFFFFFu, w[4] = {0, 0, 0, 0};
+    if (j >= 0 && j < (int64_t)a.count) {
+      pos = a.sorted[j];
+      load16_unaligned(a.data + a.origin + pos, w);
+      key = hash_key_from_words(a.hash_type, a.key_bits, w[0], w[1]);
+    }
+    s_pos[i] = pos; s_key[i] = key; s_d0[i] = w[0]; s_d1[i] = w[1]; s_d2[i] = w[2]; s_d3[i] = w[3];
+  }
+  __syncthreads();
+  const uint32_t i = threadIdx.x + (uint32_t)a.depth;
+  const uint32_t prel = s_pos[i];
+  if (prel == 0xFFFFFFFFu || prel < a.payload_begin) return;
+  const uint32_t p = a.origin + prel;
+  const uint32_t maxl = bmin(a.lcap, a.n - p);
+  uint32_t best_score = BRO_MIN_SCORE, best_len = 0, best_dist = 0;
+  if (maxl >= 4) {
+    const uint32_t key = s_key[i];
+    const uint32_t max_backward = bmin(p, a.max_backward);
+    const uint32_t m0 = s_d0[i], m1 = s_d1[i], m2 = s_d2[i], m3 = s_d3[i];
+    for (uint32_t c = 1; c <= (uint32_t)a.depth; ++c) {
+      const uint32_t ci = i - c;
+      if (s_key[ci] != key) break;
+      const uint32_t backward = prel - s_pos[ci];
+      if (backward > max_backward) break;
+      uint32_t x = s_d0[ci] ^ m0;
+      uint32_t len;
+      if (x) len = (uint32_t)(__ffs((int)x) - 1) >> 3;
+      else {
+        x = s_d1[ci] ^ m1;
+        if (x) len = 4 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+        else {
+          x = s_d2[ci] ^ m2;
+          if (x) len = 8 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+          else {
+            x = s_d3[ci] ^ m3;
+            if (x) len = 12 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+            else {
+              len = 16;
+              const uint8_t* pa = a.data + p;
+              const uint8_t* pb = pa - backward;
+              while (len < maxl && pa[len] == pb[len]) ++len;
+            }
+          }
+        }
+      }
+      if (len > maxl) len = maxl;
+      if (len >= 4) {
+        uint32_t score = score_regular(a.hash_type, len, backward);
+        if (score > best_score) { best_score = score; best_len = len; best_dist = backward; }
+        if (len == maxl) break;
+      }
+    }
+  }
+  a.best[p] = best_len ? ((best_dist << 8) | best_len) : 0u;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Parse: one thread per unit.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_parse(Workspace W) {
+  uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= W.num_units) return;
+  const EncParams& P = W.P;
+  uint32_t s = u * P.unit, e = bmin(P.n, s + P.unit), tail, ncopy;
+  const uint32_t cu = P.unit / 2 + 1;
+  W.unit_ncmd[u] = parse_unit(P, W.data, W.best, s, e, W.raw + (size_t)u * cu, &tail, &ncopy);
+  W.unit_tail[u] = tail;
+  W.unit_ncopy[u] = ncopy;
+}
+
+__device__ __forceinline__ UnitView unit_view(const Workspace& W) {
+  UnitView V;
+  V.raw = W.raw; V.ncmd = W.unit_ncmd; V.tail = W.unit_tail;
+  V.cu = W.P.unit / 2 + 1; V.unit = W.P.unit; V.n = W.P.n;
+  return V;
+}
+
+// block-wide exclusive scan helper (blockDim.x == 1024), returns exclusive prefix and total via smem
+__device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* s_warp, uint32_t* total) {
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= (uint32_t)o) x += y;
+  }
+  if (lane == 31) s_warp[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = s_warp[lane];
+    uint32_t xs = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, xs, o);
+      if (lane >= (uint32_t)o) xs += y;
+    }
+    s_warp[lane] = xs - w;
+    if (lane == 31) s_warp[32] = xs;
+  }
+  __syncthreads();
+  uint32_t r = s_warp[wid] + x - v;
+  *total = s_warp[32];
+  __syncthreads();
+  return r;
+}
+
+// One CTA (1024 threads) per metablock: per-unit final command counts and literal counts -> exclusive scans.
+__global__ void __launch_bounds__(1024) k_fin_count(Workspace W) {
+  __shared__ uint32_t s_warp[33];
+  const uint32_t m = blockIdx.x;
+  MBDesc& mb = W.mb[m];
+  const UnitView V = unit_view(W);
+  uint32_t cmd_run = 0, lit_run = 0;
+  for (uint32_t ub = mb.u0; ub < mb.u1; ub += 1024) {
+    uint32_t u = ub + threadIdx.x;
+    uint32_t nc = 0, nl = 0;
+    if (u < mb.u1) {
+      nc = unit_final_ncmd(V, mb.u0, mb.u1, u);
+      uint32_t ulen = bmin(W.P.n, (u + 1) * W.P.unit) - u * W.P.unit;
+      nl = ulen - W.unit_ncopy[u];
+    }
+    uint32_t tc, tl;
+    uint32_t ec = block_excl_scan_1024(nc, s_warp, &tc);
+    uint32_t el = block_excl_scan_1024(nl, s_warp, &tl);
+    if (u < mb.u1) { W.unit_cmd_off[u] = cmd_run + ec; W.unit_lit_off[u] = lit_run + el; }
+    cmd_run += tc;
+    lit_run += tl;
+  }
+  if (threadIdx.x == 0) { mb.ncmd = cmd_run; mb.nlit = lit_run; }
+}
+__global__ void __launch_bounds__(64) k_fin_write(Workspace W) {
+  uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= W.num_units) return;
+  const uint32_t m = u / W.P.mb_units;
+  const MBDesc& mb = W.mb[m];
+  const UnitView V = unit_view(W);
+  W.unit_ndist[u] = finalize_unit(V, mb.u0, mb.u1, u, W.unit_lit_off[u], W.cmds + (size_t)m * W.cmd_cap + W.unit_cmd_off[u]);
+}
+// One CTA per metablock: scan distance-symbol counts over units and add the prefix to each command.
+__global__ void __launch_bounds__(1024) k_fin_dist(Workspace W) {
+  __shared__ uint32_t s_warp[33];
+  const uint32_t m = blockIdx.x;
+  MBDesc& mb = W.mb[m];
+  uint32_t run = 0;
+  for (uint32_t ub = mb.u0; ub < mb.u1; ub += 1024) {
+    uint32_t u = ub + threadIdx.x;
+    uint32_t nd = u < mb.u1 ? W.unit_ndist[u] : 0;
+    uint32_t tot;
+    uint32_t ex = block_excl_scan_1024(nd, s_warp, &tot);
+    if (u < mb.u1) {
+      uint32_t c0 = W.unit_cmd_off[u];
+      uint32_t c1 = (u + 1 < mb.u1) ? W.unit_cmd_off[u + 1] : mb.ncmd;
+      GCmd* c = W.cmds + (size_t)m * W.cmd_cap;
+      for (uint32_t i = c0; i < c1; ++i) c[i].dist_idx += run + ex;
+    }
+    run += tot;
+  }
+  if (threadIdx.x == 0) mb.ndist = run;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Literal context decision: one CTA per metablock (encode.rs:1873-1927 in Q16).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ctx_decide(Workspace W) {
+  __shared__ CtxSampleHist sh;
+  const uint32_t m = blockIdx.x;
+  MBDesc& mb = W.mb[m];
+  uint32_t* raw = reinterpret_cast<uint32_t*>(&sh);
+  for (uint32_t i = threadIdx.x; i < sizeof(CtxSampleHist) / 4; i += blockDim.x) raw[i] = 0;
+  __syncthreads();
+  const EncParams& P = W.P;
+  if (!P.ctx_model || P.quality < 5 || mb.len < 64) {
+    if (threadIdx.x == 0) mb.ctx_map_id = CTXMAP_NONE;
+    return;
+  }
+  const bool complex_map = P.size_hint >= (1u << 20);
+  const uint32_t nstrides = (mb.len - 64) / 4096 + 1;
+  for (uint32_t s = threadIdx.x; s < nstrides; s += blockDim.x) {
+    // one stride per thread into a private histogram would not fit; accumulate with shared atomics
+    const uint8_t* d = W.data;
+    uint32_t sp = mb.start + s * 4096;
+    if (complex_map) {
+      uint8_t prev2 = d[sp], prev1 = d[sp + 1];
+      for (uint32_t pos = sp + 2; pos < sp + 64; ++pos) {
+        uint8_t lit = d[pos];
+        uint32_t cx = ctxmap_lookup(CTXMAP_COMPLEX13, context_utf8(prev1, prev2));
+        atomicAdd(&sh.total, 1u);
+        atomicAdd(&sh.combined[lit >> 3], 1u);
+        atomicAdd(&sh.ctx[cx][lit >> 3], 1u);
+        prev2 = prev1;
+        prev1 = lit;
+      }
+    }
+    uint32_t prev = (d[sp] >> 6) == 0 ? 0u : ((d[sp] >> 6) - 1u) * 3u;
+    for (uint32_t pos = sp + 1; pos < sp + 64; ++pos) {
+      uint32_t cl = d[pos] >> 6;
+      uint32_t l = cl == 0 ? 0u : cl - 1u;
+      atomicAdd(&sh.bigram[prev + l], 1u);
+      prev = l * 3u;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) mb.ctx_map_id = ctx_decide_from_hist(P.quality, P.size_hint, &sh, W.lut);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Symbol streams: one thread per command.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_symbols(Workspace W) {
+  const uint32_t m = blockIdx.y;
+  const MBDesc& mb = W.mb[m];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= mb.ncmd) return;
+  const GCmd c = W.cmds[(size_t)m * W.cmd_cap + i];
+  W.cmd_syms[(size_t)m * W.cmd_cap + i] = c.cmd_prefix;
+  if (c.copy_len != 0 && c.cmd_prefix >= 128) W.dist_syms[(size_t)m * W.cmd_cap + c.dist_idx] = c.dist_prefix & 0x3ffu;
+  const uint8_t* d = W.data;
+  uint16_t* ls = W.lit_syms + mb.start + c.lit_idx;
+  const int id = mb.ctx_map_id;
+  uint8_t p1 = (W.P.abs_base || c.pos >= 1) ? d[(int64_t)c.pos - 1] : 0, p2 = (W.P.abs_base || c.pos >= 2) ? d[(int64_t)c.pos - 2] : 0;
+  for (uint32_t j = 0; j < c.insert_len; ++j) {
+    uint8_t lit = d[c.pos + j];
+    uint32_t cx = id ? ctxmap_lookup(id, context_utf8(p1, p2)) : 0u;
+    ls[j] = (uint16_t)(lit | (cx << 8));
+    p2 = p1;
+    p1 = lit;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Histograms / block split.  grid = (num_mb, 3 categories).
+// k_split_simple: one block type per category (split disabled).
+// ---------------------------------------------------------------------------------------------------
+struct CatInfo {
+  const uint16_t* syms;
+  uint32_t count, A, nctx, min_block, thr_bits, max_types;
+  uint8_t* types;
+  uint32_t *lengths, *starts, *hist, *counts;  // counts -> {num_blocks, num_types}
+};
+__device__ __forceinline__ CatInfo cat_info(const Workspace& W, uint32_t m, int cat) {
+  CatInfo c;
+  const MBDesc& mb = W.mb[m];
+  if (cat == 0) {
+    c.syms = W.lit_syms + mb.start; c.count = mb.nlit; c.A = 256; c.nctx = ctxmap_num_contexts(mb.ctx_map_id);
+    c.min_block = 512; c.thr_bits = 400; c.max_types = c.nctx == 1 ? 256u : 256u / c.nctx;
+    c.types = W.lit_types + (size_t)m * W.lit_blk_cap; c.lengths = W.lit_lengths + (size_t)m * W.lit_blk_cap;
+    c.starts = W.lit_starts + (size_t)m * W.lit_blk_cap;
+    c.hist = W.lit_hist + (size_t)m * (W.max_lit_trees + 13) * 256; c.counts = W.split_counts + (size_t)m * 6;
+  } else if (cat == 1) {
+    c.syms = W.cmd_syms + (size_t)m * W.cmd_cap; c.count = mb.ncmd; c.A = 704; c.nctx = 1;
+    c.min_block = 1024; c.thr_bits = 500; c.max_types = 256;
+    c.types = W.cmd_types + (size_t)m * W.cmd_blk_cap; c.lengths = W.cmd_lengths + (size_t)m * W.cmd_blk_cap;
+    c.starts = W.cmd_starts + (size_t)m * W.cmd_blk_cap;
+    c.hist = W.cmd_hist + (size_t)m * (W.max_cmd_types + 1) * 704; c.counts = W.split_counts + (size_t)m * 6 + 2;
+  } else {
+    c.syms = W.dist_syms + (size_t)m * W.cmd_cap; c.count = mb.ndist; c.A = 64; c.nctx = 1;
+    c.min_block = 512; c.thr_bits = 100; c.max_types = 256;
+    c.types = W.dist_types + (size_t)m * W.dist_blk_cap; c.lengths = W.dist_lengths + (size_t)m * W.dist_blk_cap;
+    c.starts = W.dist_starts + (size_t)m * W.dist_blk_cap;
+    c.hist = W.dist_hist + (size_t)m * (W.max_dist_types + 1) * 64; c.counts = W.split_counts + (size_t)m * 6 + 4;
+  }
+  if (c.max_types > (cat == 0 ? W.max_lit_trees / c.nctx : (cat == 1 ? W.max_cmd_types : W.max_dist_types)))
+    c.max_types = (cat == 0 ? W.max_lit_trees / c.nctx : (cat == 1 ? W.max_cmd_types : W.max_dist_types));
+  return c;
+}
+
+__global__ void __launch_bounds__(512) k_split_simple(Workspace W) {
+  __shared__ uint32_t sh[13 * 256];
+  const uint32_t m = blockIdx.x;
+  const CatInfo c = cat_info(W, m, (int)blockIdx.y);
+  const uint32_t HA = c.nctx * c.A;
+  for (uint32_t i = threadIdx.x; i < HA; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < c.count; i += blockDim.x) {
+    uint32_t s = c.syms[i];
+    uint32_t sym = c.nctx == 1 ? s : (s & 0xFFu) + (s >> 8) * c.A;
+    atomicAdd(&sh[sym], 1u);
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < HA; i += blockDim.x) c.hist[i] = sh[i];
+  if (threadIdx.x == 0) {
+    c.types[0] = 0;
+    c.lengths[0] = c.count < c.min_block ? c.min_block : c.count;
+    c.starts[0] = 0;
+    c.counts[0] = 1;
+    c.counts[1] = 1;
+  }
+}
+
+// Greedy splitter: one CTA per (metablock, category); the symbol stream is consumed block by block, histograms
+// live in global memory (L2 resident), entropies are reduced in parallel, thread 0 takes the decision with the
+// same split_decide() the CPU model uses.
+#define SPLIT_THREADS 512
+#define SPLIT_WARPS (SPLIT_THREADS / 32)
+
+__global__ void __launch_bounds__(SPLIT_THREADS) k_split_greedy(Workspace W) {
+  __shared__ uint64_t s_part[13][3][SPLIT_WARPS];   // sum c*log2(c) partials: pending, pending+last0, pending+last1
+  __shared__ uint32_t s_cnt[13][3][SPLIT_WARPS];    // total counts partials
+  __shared__ uint64_t s_e[3][13];
+  __shared__ SplitState st;
+  __shared__ int s_action;
+  __shared__ uint32_t s_nblocks, s_pending_slot;
+  const uint32_t m = blockIdx.x;
+  const CatInfo c = cat_info(W, m, (int)blockIdx.y);
+  const uint32_t A = c.A, nctx = c.nctx, HA = nctx * A;
+  const uint32_t* lut = W.lut;
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    memset(&st, 0, sizeof(st));
+    st.target_block_size = c.min_block;
+    s_nblocks = 0;
+  }
+  for (uint32_t i = threadIdx.x; i < HA; i += SPLIT_THREADS) c.hist[i] = 0;  // pending slot 0
+  __syncthreads();
+  uint32_t consumed = 0;
+  for (;;) {
+    const uint32_t target = st.target_block_size;
+    const uint32_t remaining = c.count - consumed;
+    const bool is_final = remaining < target;   // the last call takes whatever is left (possibly nothing)
+    const uint32_t take = is_final ? remaining : target;
+    const uint32_t nb = st.num_blocks;
+    uint32_t* cur = c.hist + (size_t)st.num_types * HA;
+    const uint32_t* l0 = c.hist + (size_t)st.last_type[0] * HA;
+    const uint32_t* l1 = c.hist + (size_t)st.last_type[1] * HA;
+    for (uint32_t i = threadIdx.x; i < take; i += SPLIT_THREADS) {
+      uint32_t sv = c.syms[consumed + i];
+      uint32_t sym = nctx == 1 ? sv : (sv & 0xFFu) + (sv >> 8) * A;
+      atomicAdd(&cur[sym], 1u);
+    }
+    __syncthreads();
+    consumed += take;
+    for (uint32_t cx = 0; cx < nctx; ++cx) {
+      uint64_t a0 = 0, a1 = 0, a2 = 0;
+      uint32_t t0 = 0, t1 = 0, t2 = 0;
+      for (uint32_t k = threadIdx.x; k < A; k += SPLIT_THREADS) {
+        uint32_t v = cur[cx * A + k];
+        if (v) { a0 += xlog2x_q16(lut, v); t0 += v; }
+        if (nb) {
+          uint32_t v0 = v + l0[cx * A + k], v1 = v + l1[cx * A + k];
+          if (v0) { a1 += xlog2x_q16(lut, v0); t1 += v0; }
+          if (v1) { a2 += xlog2x_q16(lut, v1); t2 += v1; }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_down_sync(0xffffffffu, a0, o); a1 += __shfl_down_sync(0xffffffffu, a1, o);
+        a2 += __shfl_down_sync(0xffffffffu, a2, o); t0 += __shfl_down_sync(0xffffffffu, t0, o);
+        t1 += __shfl_down_sync(0xffffffffu, t1, o); t2 += __shfl_down_sync(0xffffffffu, t2, o);
+      }
+      if (lane == 0) {
+        s_part[cx][0][wid] = a0; s_part[cx][1][wid] = a1; s_part[cx][2][wid] = a2;
+        s_cnt[cx][0][wid] = t0; s_cnt[cx][1][wid] = t1; s_cnt[cx][2][wid] = t2;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 * nctx) {
+      const uint32_t cx = threadIdx.x / 3, q = threadIdx.x % 3;
+      uint64_t a = 0;
+      uint32_t t = 0;
+      for (int w = 0; w < SPLIT_WARPS; ++w) { a += s_part[cx][q][w]; t += s_cnt[cx][q][w]; }
+      s_e[q][cx] = bits_entropy_q16(a, t, lut);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t bs = take < c.min_block ? c.min_block : take;
+      uint32_t old_types = st.num_types;
+      s_pending_slot = old_types;
+      SplitAction act = split_decide(st, nctx, c.max_types, (uint64_t)c.thr_bits << 16, c.min_block, s_e[0], s_e[1], s_e[2]);
+      s_action = (int)act;
+      uint32_t b = s_nblocks;
+      if (act == SPLIT_FIRST) { c.types[b] = 0; c.lengths[b] = bs; s_nblocks = b + 1; }
+      else if (act == SPLIT_NEW_TYPE) { c.types[b] = (uint8_t)old_types; c.lengths[b] = bs; s_nblocks = b + 1; }
+      else if (act == SPLIT_SECOND_LAST) { c.types[b] = (uint8_t)st.last_type[0]; c.lengths[b] = bs; s_nblocks = b + 1; }
+      else { c.lengths[b - 1] += bs; }
+    }
+    __syncthreads();
+    {
+      const int act = s_action;
+      uint32_t* pend = c.hist + (size_t)s_pending_slot * HA;
+      if (act == SPLIT_FIRST || act == SPLIT_NEW_TYPE) {
+        uint32_t* np = c.hist + (size_t)st.num_types * HA;  // new pending slot
+        for (uint32_t i = threadIdx.x; i < HA; i += SPLIT_THREADS) np[i] = 0;
+      } else {
+        // merge pending into the (new) last histogram; after SPLIT_SECOND_LAST last_type[0] is the old second-last
+        uint32_t* dst = c.hist + (size_t)st.last_type[0] * HA;
+        for (uint32_t i = threadIdx.x; i < HA; i += SPLIT_THREADS) { dst[i] += pend[i]; pend[i] = 0; }
+      }
+    }
+    __syncthreads();
+    if (is_final) break;
+  }
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0;
+    for (uint32_t b = 0; b < s_nblocks; ++b) { c.starts[b] = acc; acc += c.lengths[b]; }
+    c.counts[0] = s_nblocks;
+    c.counts[1] = st.num_types;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Header: one thread per metablock builds all prefix codes and the metablock header bits.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_header(Workspace W) {
+  const uint32_t m = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  MBDesc& mb = W.mb[m];
+  const EncParams& P = W.P;
+  const uint32_t nctx = ctxmap_num_contexts(mb.ctx_map_id);
+  HuffStoreWs* ws = W.huff_ws + m;
+  SplitView lv = make_view(W, m, 0), cv = make_view(W, m, 1), dv = make_view(W, m, 2);
+  uint32_t* lh = W.lit_hist + (size_t)m * (W.max_lit_trees + 13) * 256;
+  uint32_t* ch = W.cmd_hist + (size_t)m * (W.max_cmd_types + 1) * 704;
+  uint32_t* dh = W.dist_hist + (size_t)m * (W.max_dist_types + 1) * 64;
+  if (P.use_rle_opt) {
+    uint8_t* good = ws->rle;
+    for (uint32_t t = 0; t < lv.num_types * nctx; ++t) huff_optimize_counts_for_rle(256, lh + (size_t)t * 256, good);
+    for (uint32_t t = 0; t < cv.num_types; ++t) huff_optimize_counts_for_rle(704, ch + (size_t)t * 704, good);
+    for (uint32_t t = 0; t < dv.num_types; ++t) huff_optimize_counts_for_rle(64, dh + (size_t)t * 64, good);
+  }
+  BitWriter bw;
+  bw.init(W.hdr + (size_t)m * W.hdr_cap);
+  store_compressed_metablock_header(bw, false, mb.len);
+  SplitCode* sc = W.split_codes + (size_t)m * 3;
+  store_block_split_code(bw, lv, sc + 0, ws);
+  store_block_split_code(bw, cv, sc + 1, ws);
+  store_block_split_code(bw, dv, sc + 2, ws);
+  bw.put(2, 0);
+  bw.put(4, 0);
+  for (uint32_t i = 0; i < lv.num_types; ++i) bw.put(2, 2);
+  if (mb.ctx_map_id == CTXMAP_NONE) store_trivial_context_map(bw, lv.num_types, 6, ws);
+  else store_static_literal_context_map(bw, lv.num_types, mb.ctx_map_id, W.ctxmap_ws + (size_t)m * 256 * 64, ws);
+  store_trivial_context_map(bw, dv.num_types, 2, ws);
+  uint8_t* ld = W.lit_depth + (size_t)m * W.max_lit_trees * 256; uint16_t* lc = W.lit_code + (size_t)m * W.max_lit_trees * 256;
+  uint8_t* cd = W.cmd_depth + (size_t)m * W.max_cmd_types * 704; uint16_t* cc = W.cmd_code + (size_t)m * W.max_cmd_types * 704;
+  uint8_t* dd = W.dist_depth + (size_t)m * W.max_dist_types * 64; uint16_t* dcode = W.dist_code + (size_t)m * W.max_dist_types * 64;
+  for (uint32_t t = 0; t < lv.num_types * nctx; ++t) huff_build_and_store(bw, lh + (size_t)t * 256, 256, 256, ws, ld + (size_t)t * 256, lc + (size_t)t * 256);
+  for (uint32_t t = 0; t < cv.num_types; ++t) huff_build_and_store(bw, ch + (size_t)t * 704, 704, 704, ws, cd + (size_t)t * 704, cc + (size_t)t * 704);
+  for (uint32_t t = 0; t < dv.num_types; ++t) huff_build_and_store(bw, dh + (size_t)t * 64, 64, 64, ws, dd + (size_t)t * 64, dcode + (size_t)t * 64);
+  bw.flush_partial();
+  mb.hdr_bits = (uint32_t)bw.bit_pos();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Emission.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bitlen(Workspace W) {
+  const uint32_t m = blockIdx.y;
+  const MBDesc& mb = W.mb[m];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= mb.ncmd) return;
+  const MetaCodes mc = make_codes(W, m);
+  const GCmd g = W.cmds[(size_t)m * W.cmd_cap + i];
+  CountWriter w;
+  w.bits = 0;
+  emit_command(w, mc, g.as_cmd(), i, g.lit_idx, g.dist_idx, W.data, g.pos, W.P.abs_base);
+  W.cmd_bits[(size_t)m * W.cmd_cap + i] = (uint32_t)w.bits;
+}
+// One CTA per metablock: exclusive scan of command bit lengths (in place), total -> body_bits.
+__global__ void __launch_bounds__(1024) k_bitscan(Workspace W) {
+  __shared__ uint32_t s_warp[33];
+  const uint32_t m = blockIdx.x;
+  MBDesc& mb = W.mb[m];
+  uint32_t* bits = W.cmd_bits + (size_t)m * W.cmd_cap;
+  uint64_t run = 0;
+  for (uint32_t base = 0; base < mb.ncmd; base += 1024) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < mb.ncmd ? bits[i] : 0;
+    uint32_t tot;
+    uint32_t ex = block_excl_scan_1024(v, s_warp, &tot);
+    if (i < mb.ncmd) bits[i] = (uint32_t)(run + ex);  // body of a metablock stays below 2^32 bits
+    run += tot;
+  }
+  if (threadIdx.x == 0) mb.body_bits = run;
+}
+
+struct AtomicOrWriter {
+  uint32_t* out;
+  uint64_t word;
+  uint64_t acc;
+  uint32_t nacc;
+  __device__ __forceinline__ void init(uint32_t* o, uint64_t bitpos) { out = o; word = bitpos >> 5; nacc = (uint32_t)(bitpos & 31); acc = 0; }
+  __device__ __forceinline__ void put(uint32_t n, uint64_t v) {
+    acc |= v << nacc;
+    nacc += n;
+    if (nacc >= 32) {
+      atomicOr(&out[word++], (uint32_t)acc);
+      acc >>= 32;
+      nacc -= 32;
+    }
+  }
+  __device__ __forceinline__ void flush() { if (nacc) atomicOr(&out[word], (uint32_t)acc); }
+};
+
+// Single thread: raw/compressed decision per metablock, stream layout, stream header / trailer / padding bits.
+__global__ void k_layout(Workspace W, int first, int last, int byte_align) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const EncParams& P = W.P;
+  uint64_t pos = *W.total_bits;
+  if (first) {
+    AtomicOrWriter w;
+    w.init(W.out, pos);
+    if (P.lgwin == 16) { w.put(1, 0); pos += 1; }
+    else if (P.lgwin == 17) { w.put(7, 1); pos += 7; }
+    else if (P.lgwin > 17) { w.put(4, (uint64_t)(((P.lgwin - 17) << 1) | 1)); pos += 4; }
+    else { w.put(7, (uint64_t)(((P.lgwin - 8) << 4) | 1)); pos += 7; }
+    w.flush();
+  }
+  for (uint32_t m = 0; m < W.num_mb; ++m) {
+    MBDesc& mb = W.mb[m];
+    uint64_t comp_bits = (uint64_t)mb.hdr_bits + mb.body_bits;
+    uint64_t raw_hdr = raw_metablock_header_bits(mb.len);
+    uint64_t raw_bits = ((pos + raw_hdr + 7) & ~7ull) - pos + 8ull * mb.len;
+    mb.raw = comp_bits > raw_bits ? 1u : 0u;
+    mb.out_bitpos = pos;
+    pos += mb.raw ? raw_bits : comp_bits;
+  }
+  if (last) {
+    AtomicOrWriter t;
+    t.init(W.out, pos);
+    t.put(2, 3);  // ISLAST = 1, ISLASTEMPTY = 1
+    t.flush();
+    pos += 2;
+  } else if (byte_align && (pos & 7)) {
+    AtomicOrWriter t;  // empty metadata metablock (brotli_bit_stream.rs:2840-2845), then zero padding
+    t.init(W.out, pos);
+    t.put(6, 6);
+    t.flush();
+    pos = (pos + 6 + 7) & ~7ull;
+  }
+  *W.total_bits = pos;
+}
+
+__global__ void __launch_bounds__(256) k_emit_header(Workspace W) {
+  const uint32_t m = blockIdx.x;
+  const MBDesc& mb = W.mb[m];
+  if (mb.raw) return;
+  const uint8_t* h = W.hdr + (size_t)m * W.hdr_cap;
+  const uint32_t nbytes = (mb.hdr_bits + 7) / 8;
+  // hdr_cap is a multiple of 4 and the buffer is zero beyond hdr_bits within the last byte
+  for (uint32_t i = threadIdx.x; i * 4 < nbytes; i += blockDim.x) {
+    uint32_t v = 0;
+    for (uint32_t k = 0; k < 4; ++k) {
+      uint32_t idx = i * 4 + k;
+      uint32_t byte = idx < nbytes ? h[idx] : 0u;
+      if (idx == nbytes - 1 && (mb.hdr_bits & 7)) byte &= (1u << (mb.hdr_bits & 7)) - 1u;
+      v |= byte << (8 * k);
+    }
+    if (v == 0) continue;
+    uint64_t bitpos = mb.out_bitpos + (uint64_t)i * 32;
+    uint64_t word = bitpos >> 5;
+    uint32_t sh = (uint32_t)(bitpos & 31);
+    atomicOr(&W.out[word], v << sh);
+    if (sh) atomicOr(&W.out[word + 1], v >> (32 - sh));
+  }
+}
+__global__ void __launch_bounds__(256) k_emit_body(Workspace W) {
+  const uint32_t m = blockIdx.y;
+  const MBDesc& mb = W.mb[m];
+  if (mb.raw) return;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= mb.ncmd) return;
+  const MetaCodes mc = make_codes(W, m);
+  const GCmd g = W.cmds[(size_t)m * W.cmd_cap + i];
+  AtomicOrWriter w;
+  w.init(W.out, mb.out_bitpos + mb.hdr_bits + W.cmd_bits[(size_t)m * W.cmd_cap + i]);
+  emit_command(w, mc, g.as_cmd(), i, g.lit_idx, g.dist_idx, W.data, g.pos, W.P.abs_base);
+  w.flush();
+}
+__global__ void __launch_bounds__(256) k_emit_raw(Workspace W) {
+  const uint32_t m = blockIdx.y;
+  const MBDesc& mb = W.mb[m];
+  if (!mb.raw) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    AtomicOrWriter w;
+    w.init(W.out, mb.out_bitpos);
+    uint32_t lg = mb.len == 1 ? 1u : log2_floor_nz(mb.len - 1) + 1u;
+    uint32_t mnibbles = (lg < 16 ? 16u : lg + 3u) / 4u;
+    w.put(1, 0);
+    w.put(2, mnibbles - 4);
+    w.put(mnibbles * 4, mb.len - 1);
+    w.put(1, 1);
+    w.flush();
+  }
+  const uint64_t byte0 = (mb.out_bitpos + raw_metablock_header_bits(mb.len) + 7) >> 3;
+  uint8_t* ob = reinterpret_cast<uint8_t*>(W.out);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < mb.len; i += gridDim.x * blockDim.x)
+    ob[byte0 + i] = W.data[mb.start + i];
+}
+
+}  // namespace bro

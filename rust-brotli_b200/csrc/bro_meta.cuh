@@ -217,7 +217,7 @@ BRO_HD uint32_t find_block(const uint32_t* starts, uint32_t num_blocks, uint32_t
 // pos = input position of the first literal of the command.
 template <typename W>
 BRO_HD_NOINLINE void emit_command(W& w, const MetaCodes& mc, const Cmd& c, uint32_t cmd_idx, uint32_t lit_idx,
-                                  uint32_t dist_idx, const uint8_t* data, uint32_t pos) {
+                                  uint32_t dist_idx, const uint8_t* data, uint32_t pos, uint32_t abs_base) {
   {
     uint32_t b = 0;
     if (mc.cmd.num_blocks > 1) {
@@ -243,7 +243,7 @@ BRO_HD_NOINLINE void emit_command(W& w, const MetaCodes& mc, const Cmd& c, uint3
       if (b > 0 && mc.lit.starts[b] == lit_idx) put_block_switch(w, mc.lit, *mc.lit_sc, b, false);
     }
     uint32_t tbase = mc.lit.types[b] * mc.nctx;
-    uint8_t p1 = pos >= 1 ? data[pos - 1] : 0, p2 = pos >= 2 ? data[pos - 2] : 0;
+    uint8_t p1 = (abs_base || pos >= 1) ? data[(int64_t)pos - 1] : 0, p2 = (abs_base || pos >= 2) ? data[(int64_t)pos - 2] : 0;
     for (uint32_t j = 0; j < c.insert_len; ++j) {
       if (lit_idx + j == bend) {
         ++b;

@@ -22,7 +22,8 @@ struct EncParams {
   uint32_t unit;      // parse unit size in bytes
   uint32_t mb_units;  // parse units per metablock
   uint32_t max_backward;  // (1 << lgwin) - 16
-  uint32_t n;         // input size
+  uint32_t n;         // size of the range being compressed (positions are relative to its start)
+  uint32_t abs_base;  // absolute stream position of relative position 0 (window limit at the stream start)
   uint32_t size_hint;
   int use_rle_opt;    // apply BrotliOptimizeHuffmanCountsForRle
   int split;          // greedy block splitting on/off
@@ -80,7 +81,7 @@ BRO_HD int32_t cache_candidate(const int32_t* dc, int i) {
 // Best match at pos: last-distance probes (serial state) combined with the precomputed bucket candidate.
 BRO_HD_NOINLINE bool find_match(const EncParams& P, const uint8_t* data, const uint32_t* best, const int32_t* dc,
                                 uint32_t pos, uint32_t max_len, Match* out) {
-  const uint32_t max_backward = bmin(pos, P.max_backward);
+  const uint32_t max_backward = (P.abs_base >= P.max_backward) ? P.max_backward : bmin(pos + P.abs_base, P.max_backward);
   uint32_t best_score = BRO_MIN_SCORE, best_len = 0, best_dist = 0;
   bool found = false;
   const uint8_t* cur = data + pos;

@@ -243,7 +243,7 @@ void stage_bitlen(Model& M, MetaBlock& mb) {
   uint64_t total = 0;
   for (size_t i = 0; i < mb.cmds.size(); ++i) {
     CountWriter w{0};
-    emit_command(w, mc, mb.cmds[i].as_cmd(), (uint32_t)i, mb.cmds[i].lit_idx, mb.cmds[i].dist_idx, M.data.data(), mb.cmds[i].pos);
+    emit_command(w, mc, mb.cmds[i].as_cmd(), (uint32_t)i, mb.cmds[i].lit_idx, mb.cmds[i].dist_idx, M.data.data(), mb.cmds[i].pos, 0);
     mb.cmd_bitpos[i] = total;
     total += w.bits;
   }
@@ -369,7 +369,7 @@ size_t gpu_model_compress(const EncParams* Pin, const uint8_t* input, uint8_t* o
       MetaCodes mc = codes_of(mb, lv, cv, dv);
       for (size_t i = 0; i < mb.cmds.size(); ++i) {
         PlainOrWriter cw{out, base + mb.cmd_bitpos[i]};
-        emit_command(cw, mc, mb.cmds[i].as_cmd(), (uint32_t)i, mb.cmds[i].lit_idx, mb.cmds[i].dist_idx, M.data.data(), mb.cmds[i].pos);
+        emit_command(cw, mc, mb.cmds[i].as_cmd(), (uint32_t)i, mb.cmds[i].lit_idx, mb.cmds[i].dist_idx, M.data.data(), mb.cmds[i].pos, 0);
       }
       w.pos = base + mb.body_bits;
     }
