@@ -1,0 +1,56 @@
+"""CPU: the sequential model of the GPU pipeline (tools/gpu_model.cpp, built from the same host/device headers as the
+kernels).  It must produce valid brotli, stay within +0.5 % of the reference restatement, and match its goldens --
+the GPU tests then assert that the kernels reproduce these streams bit for bit."""
+import hashlib
+
+import pytest
+
+from conftest import golden_bytes
+from oracle.harness import sys_decompress
+
+FILES = ["alice29.txt", "asyoulik.txt", "random_then_unicode", "quickfox_repeated", "random_org_10k.bin", "backward65536",
+         "64x", "ukkonooa", "monkey", "x", "xyzzy", "10x10y", "aaabaaaa", "empty", "quickfox", "compressed_file"]
+
+
+@pytest.mark.parametrize("name", FILES)
+@pytest.mark.parametrize("q,w", [(5, 20), (5, 22), (7, 22), (9, 22), (9, 16), (5, 18)])
+def test_model_golden_roundtrip_and_size(model, golden_table, name, q, w):
+    d = golden_bytes(name)
+    c, _ = model.compress(d, q, w)
+    assert sys_decompress(c, len(d)) == d
+    g = golden_table["%s|q%d|w%d" % (name, q, w)]
+    assert hashlib.sha256(c).hexdigest() == g["model_sha256"]
+    # size parity with the reference restatement: <= +0.5 % (absolute slack of 8 bytes for tiny streams)
+    assert len(c) <= g["oracle_size"] * 1.005 + 8
+
+
+@pytest.mark.parametrize("shards", [1, 2, 3, 5])
+def test_model_sharded_seams(model, shards):
+    """compress_multi split rule (threading/mod.rs:333) with byte-aligned seams: concatenation must decode."""
+    d = golden_bytes("random_then_unicode")
+    n = len(d)
+    parts = []
+    for i in range(shards):
+        a, b = i * n // shards, (i + 1) * n // shards
+        c, _ = model.compress_range(d, a, b - a, 5, 22, i == 0, i + 1 == shards, i + 1 != shards)
+        parts.append(c)
+    out = b"".join(parts)
+    assert sys_decompress(out, n) == d
+    if shards == 3:
+        assert len(out) <= 144325  # src/bin/test_threading.rs:101 bound for 3 threads q5
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 7, 8, 9, 63, 64, 65, 4095, 4096, 4097, 8191, 8192, 12289])
+def test_model_edge_sizes(model, n):
+    d = (golden_bytes("alice29.txt") * 2)[:n]
+    c, _ = model.compress(d, 5, 22)
+    assert sys_decompress(c, max(n, 1)) == d
+
+
+def test_model_options(model):
+    d = golden_bytes("asyoulik.txt")
+    base, _ = model.compress(d, 5, 22)
+    for kw in ({"split": 0}, {"ctx_model": 0}, {"use_rle_opt": 0}, {"unit": 2048}, {"unit": 16384}, {"lcap": 32}, {"mb_units": 8}):
+        c, _ = model.compress(d, 5, 22, **kw)
+        assert sys_decompress(c, len(d)) == d
+        assert len(c) < len(base) * 1.03

@@ -41,6 +41,8 @@ struct Model {
   std::vector<uint32_t> best;
   std::vector<RawCmd> raw;
   std::vector<uint32_t> unit_ncmd, unit_tail, unit_ncopy;
+  uint32_t data_shift = 0;  // range start inside `data`
+  const uint8_t* d() const { return data.data() + data_shift; }
 };
 
 void stage_match(Model& M) {
@@ -91,7 +93,7 @@ void stage_parse(Model& M) {
   M.unit_ncopy.assign(NU, 0);
   for (uint32_t u = 0; u < NU; ++u) {
     uint32_t s = u * P.unit, e = bmin(P.n, s + P.unit), tail, ncopy;
-    M.unit_ncmd[u] = parse_unit(P, M.data.data(), M.best.data(), s, e, &M.raw[(size_t)u * CU], &tail, &ncopy);
+    M.unit_ncmd[u] = parse_unit(P, M.d(), M.best.data(), s, e, &M.raw[(size_t)u * CU], &tail, &ncopy);
     M.unit_tail[u] = tail;
     M.unit_ncopy[u] = ncopy;
   }
@@ -141,12 +143,12 @@ void stage_ctx_decide(Model& M, MetaBlock& mb) {
   const EncParams& P = M.P;
   mb.ctx_map_id = CTXMAP_NONE;
   if (!P.ctx_model) return;
-  mb.ctx_map_id = decide_literal_context_map(P.quality, P.size_hint, M.data.data(), mb.start, mb.len, M.lut.data());
+  mb.ctx_map_id = decide_literal_context_map(P.quality, P.size_hint, M.d(), mb.start, mb.len, M.lut.data());
 }
 
 void stage_split_and_histograms(Model& M, MetaBlock& mb) {
   const EncParams& P = M.P;
-  const uint8_t* d = M.data.data();
+  const uint8_t* d = M.d();
   const uint32_t nctx = ctxmap_num_contexts(mb.ctx_map_id);
   // symbol streams
   std::vector<uint16_t> lits(mb.nlit);   // literal | ctx << 8
@@ -157,7 +159,7 @@ void stage_split_and_histograms(Model& M, MetaBlock& mb) {
     uint32_t pos = c.pos;
     for (uint32_t j = 0; j < c.insert_len; ++j) {
       uint32_t p = pos + j;
-      uint8_t p1 = p >= 1 ? d[p - 1] : 0, p2 = p >= 2 ? d[p - 2] : 0;
+      uint8_t p1 = (P.abs_base || p >= 1) ? d[(int64_t)p - 1] : 0, p2 = (P.abs_base || p >= 2) ? d[(int64_t)p - 2] : 0;
       uint32_t cx = mb.ctx_map_id ? ctxmap_lookup(mb.ctx_map_id, context_utf8(p1, p2)) : 0;
       lits[c.lit_idx + j] = (uint16_t)(d[p] | (cx << 8));
     }
@@ -243,7 +245,7 @@ void stage_bitlen(Model& M, MetaBlock& mb) {
   uint64_t total = 0;
   for (size_t i = 0; i < mb.cmds.size(); ++i) {
     CountWriter w{0};
-    emit_command(w, mc, mb.cmds[i].as_cmd(), (uint32_t)i, mb.cmds[i].lit_idx, mb.cmds[i].dist_idx, M.data.data(), mb.cmds[i].pos, 0);
+    emit_command(w, mc, mb.cmds[i].as_cmd(), (uint32_t)i, mb.cmds[i].lit_idx, mb.cmds[i].dist_idx, M.d(), mb.cmds[i].pos, M.P.abs_base);
     mb.cmd_bitpos[i] = total;
     total += w.bits;
   }
@@ -295,19 +297,43 @@ void gpu_model_fill_lut(uint32_t* lut) {
 }
 
 // Runs the whole pipeline model.  Returns compressed size in bytes (0 on failure).
+size_t gpu_model_compress_range(const EncParams* Pin, const uint8_t* input, uint32_t range_start, uint32_t range_len,
+                                int first, int last, int byte_align, uint8_t* out, size_t out_cap, ModelStats* st,
+                                uint32_t* best_out);
+
 size_t gpu_model_compress(const EncParams* Pin, const uint8_t* input, uint8_t* out, size_t out_cap, ModelStats* st,
                           uint32_t* best_out /* optional [n] */) {
+  return gpu_model_compress_range(Pin, input, 0, Pin->n, 1, 1, 0, out, out_cap, st, best_out);
+}
+
+// Mirrors b200_encoder_compress_range: Pin->n is the size of the whole stream `input`.
+size_t gpu_model_compress_range(const EncParams* Pin, const uint8_t* input, uint32_t range_start, uint32_t range_len,
+                                int first, int last, int byte_align, uint8_t* out, size_t out_cap, ModelStats* st,
+                                uint32_t* best_out) {
   Model M;
   M.P = *Pin;
-  const EncParams& P = M.P;
-  const uint32_t N = P.n;
+  const uint32_t stream_n = Pin->n;
   if (st) memset(st, 0, sizeof(*st));
-  if (N == 0) { out[0] = 6; return 1; }
-  M.data.assign((size_t)N + 320, 0);
-  memcpy(M.data.data(), input, N);
+  if (stream_n == 0 || range_len == 0) {
+    if (first && last && stream_n == 0) { out[0] = 6; return 1; }
+    return 0;
+  }
+  // match stage over the whole prefix (absolute positions), then shift everything to range-relative
+  M.P.n = range_start + range_len;
+  M.P.abs_base = 0;
+  M.data.assign((size_t)M.P.n + 320, 0);
+  memcpy(M.data.data(), input, M.P.n);
   M.lut.resize(65536);
   gpu_model_fill_lut(M.lut.data());
   stage_match(M);
+  if (range_start) {
+    M.best.erase(M.best.begin(), M.best.begin() + range_start);
+    M.data_shift = range_start;
+  }
+  M.P.n = range_len;
+  M.P.abs_base = range_start;
+  const EncParams& P = M.P;
+  const uint32_t N = P.n;
   if (best_out) memcpy(best_out, M.best.data(), (size_t)N * 4);
   stage_parse(M);
   const uint32_t NU = (N + P.unit - 1) / P.unit;
@@ -327,10 +353,12 @@ size_t gpu_model_compress(const EncParams* Pin, const uint8_t* input, uint8_t* o
   // layout: stream header, metablocks, final empty metablock
   memset(out, 0, out_cap);
   PlainOrWriter w{out, 0};
-  if (P.lgwin == 16) w.put(1, 0);
-  else if (P.lgwin == 17) w.put(7, 1);
-  else if (P.lgwin > 17) w.put(4, (uint64_t)(((P.lgwin - 17) << 1) | 1));
-  else w.put(7, (uint64_t)(((P.lgwin - 8) << 4) | 1));
+  if (first) {
+    if (P.lgwin == 16) w.put(1, 0);
+    else if (P.lgwin == 17) w.put(7, 1);
+    else if (P.lgwin > 17) w.put(4, (uint64_t)(((P.lgwin - 17) << 1) | 1));
+    else w.put(7, (uint64_t)(((P.lgwin - 8) << 4) | 1));
+  }
   for (uint32_t m = 0; m < NM; ++m) {
     MetaBlock& mb = mbs[m];
     uint64_t comp_bits = mb.hdr_bits + mb.body_bits;
@@ -358,7 +386,7 @@ size_t gpu_model_compress(const EncParams* Pin, const uint8_t* input, uint8_t* o
       w.put(mnibbles * 4, mb.len - 1);
       w.put(1, 1);
       w.pos = (w.pos + 7) & ~7ull;
-      memcpy(out + (w.pos >> 3), M.data.data() + mb.start, mb.len);
+      memcpy(out + (w.pos >> 3), M.d() + mb.start, mb.len);
       w.pos += 8ull * mb.len;
     } else {
       uint64_t base = w.pos;
@@ -369,13 +397,18 @@ size_t gpu_model_compress(const EncParams* Pin, const uint8_t* input, uint8_t* o
       MetaCodes mc = codes_of(mb, lv, cv, dv);
       for (size_t i = 0; i < mb.cmds.size(); ++i) {
         PlainOrWriter cw{out, base + mb.cmd_bitpos[i]};
-        emit_command(cw, mc, mb.cmds[i].as_cmd(), (uint32_t)i, mb.cmds[i].lit_idx, mb.cmds[i].dist_idx, M.data.data(), mb.cmds[i].pos, 0);
+        emit_command(cw, mc, mb.cmds[i].as_cmd(), (uint32_t)i, mb.cmds[i].lit_idx, mb.cmds[i].dist_idx, M.d(), mb.cmds[i].pos, M.P.abs_base);
       }
       w.pos = base + mb.body_bits;
     }
   }
-  w.put(1, 1);  // ISLAST
-  w.put(1, 1);  // ISLASTEMPTY
+  if (last) {
+    w.put(1, 1);  // ISLAST
+    w.put(1, 1);  // ISLASTEMPTY
+  } else if (byte_align && (w.pos & 7)) {
+    w.put(6, 6);
+    w.pos = (w.pos + 7) & ~7ull;
+  }
   return (size_t)((w.pos + 7) >> 3);
 }
 
