@@ -71,7 +71,7 @@ struct B200Encoder {
   // buffers
   DevBuf d_data, d_lut, d_sortA, d_sortB, d_hist, d_digit, d_best, d_raw, d_unit, d_cmds, d_cmd_bits, d_lit_syms,
       d_cmd_syms, d_dist_syms, d_mb, d_split_u8, d_split_u32, d_split_counts, d_hist_lit, d_hist_cmd, d_hist_dist,
-      d_split_codes, d_codes_u8, d_codes_u16, d_hdr, d_huff_ws, d_ctxmap_ws, d_out, d_total;
+      d_split_codes, d_codes_u8, d_codes_u16, d_hdr, d_huff_ws, d_ctxmap_ws, d_out, d_total, d_tree_ws, d_tree_bits, d_tree_nbits;
   uint8_t* h_pinned = nullptr;
   size_t h_pinned_cap = 0;
   uint64_t data_base = 0;  // absolute stream position of d_data[0]
@@ -101,7 +101,7 @@ struct B200Encoder {
     DevBuf* all[] = {&d_data, &d_lut, &d_sortA, &d_sortB, &d_hist, &d_digit, &d_best, &d_raw, &d_unit, &d_cmds, &d_cmd_bits,
                      &d_lit_syms, &d_cmd_syms, &d_dist_syms, &d_mb, &d_split_u8, &d_split_u32, &d_split_counts, &d_hist_lit,
                      &d_hist_cmd, &d_hist_dist, &d_split_codes, &d_codes_u8, &d_codes_u16, &d_hdr, &d_huff_ws, &d_ctxmap_ws,
-                     &d_out, &d_total};
+                     &d_out, &d_total, &d_tree_ws, &d_tree_bits, &d_tree_nbits};
     for (auto* b : all) b->release();
     if (h_pinned) cudaFreeHost(h_pinned);
     for (auto& e : ev_pool) cudaEventDestroy(e);
@@ -178,6 +178,10 @@ struct B200Encoder {
     if (!d_hdr.ensure((size_t)NM * W->hdr_cap)) return false;
     if (!d_huff_ws.ensure((size_t)NM * sizeof(HuffStoreWs))) return false;
     if (!d_ctxmap_ws.ensure((size_t)NM * 256 * 64 * 4)) return false;
+    const size_t tree_cap = (size_t)W->max_lit_trees + W->max_cmd_types + W->max_dist_types;
+    if (!d_tree_ws.ensure((size_t)NM * tree_cap * sizeof(HuffStoreWs))) return false;
+    if (!d_tree_bits.ensure((size_t)NM * tree_cap * TREE_SLOT_BYTES)) return false;
+    if (!d_tree_nbits.ensure((size_t)NM * tree_cap * 4)) return false;
     // sort scratch
     const uint32_t nb = std::min<uint64_t>((uint64_t)c + (1ull << P.lgwin), kBatchMax);
     const uint32_t tiles = (nb + SORT_TILE - 1) / SORT_TILE;
@@ -219,6 +223,9 @@ struct B200Encoder {
     W->hdr = d_hdr.as<uint8_t>();
     W->huff_ws = d_huff_ws.as<HuffStoreWs>();
     W->ctxmap_ws = d_ctxmap_ws.as<uint32_t>();
+    W->tree_ws = d_tree_ws.as<HuffStoreWs>();
+    W->tree_bits = d_tree_bits.as<uint8_t>();
+    W->tree_nbits = d_tree_nbits.as<uint32_t>();
     W->total_bits = d_total.as<uint64_t>();
     return true;
   }
@@ -322,10 +329,10 @@ struct B200Encoder {
       launches += 1;
     }
     mark(B200_ST_PARSE);
-    k_parse<<<(W.num_units + 63) / 64, 64, 0, stream>>>(W);
+    k_parse<<<(W.num_units + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, stream>>>(W);
     mark(B200_ST_FINALIZE);
     k_fin_count<<<W.num_mb, 1024, 0, stream>>>(W);
-    k_fin_write<<<(W.num_units + 63) / 64, 64, 0, stream>>>(W);
+    k_fin_write<<<(W.num_units + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, stream>>>(W);
     k_fin_dist<<<W.num_mb, 1024, 0, stream>>>(W);
     k_ctx_decide<<<W.num_mb, 256, 0, stream>>>(W);
     {
@@ -339,6 +346,10 @@ struct B200Encoder {
       else k_split_simple<<<g, 512, 0, stream>>>(W);
     }
     mark(B200_ST_HEADER);
+    {
+      dim3 g(W.max_lit_trees + W.max_cmd_types + W.max_dist_types, W.num_mb);
+      k_trees<<<g, 32, 0, stream>>>(W);
+    }
     k_header<<<W.num_mb, 32, 0, stream>>>(W);
     mark(B200_ST_EMIT);
     {
@@ -352,7 +363,7 @@ struct B200Encoder {
       k_emit_raw<<<gr, 256, 0, stream>>>(W);
     }
     mark(-1);
-    launches += 14;
+    launches += 15;
     CUDA_OK(cudaGetLastError());
     return true;
   }

@@ -87,6 +87,9 @@ struct Workspace {
   uint8_t* hdr;           // [num_mb][hdr_cap]
   uint32_t hdr_cap;
   HuffStoreWs* huff_ws;   // [num_mb]
+  HuffStoreWs* tree_ws;   // [num_mb][tree_cap]
+  uint8_t* tree_bits;     // [num_mb][tree_cap][TREE_SLOT_BYTES]
+  uint32_t* tree_nbits;   // [num_mb][tree_cap]
   uint32_t* ctxmap_ws;    // [num_mb][max_lit_types * 64]
   // output
   uint32_t* out;          // zero-initialised words
@@ -377,9 +380,12 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
 // ---------------------------------------------------------------------------------------------------
 // Parse: one thread per unit.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k_parse(Workspace W) {
-  uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= W.num_units) return;
+#define PARSE_WARPS 4
+__global__ void __launch_bounds__(PARSE_WARPS * 32) k_parse(Workspace W) {
+  // One parse unit per WARP: units follow unrelated control flow, so putting 32 of them in one warp serialises
+  // them (measured 8.9 ms -> see profiles/); lane 0 walks the unit.
+  uint32_t u = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);
+  if (u >= W.num_units || (threadIdx.x & 31) != 0) return;
   const EncParams& P = W.P;
   uint32_t s = u * P.unit, e = bmin(P.n, s + P.unit), tail, ncopy;
   const uint32_t cu = P.unit / 2 + 1;
@@ -448,9 +454,9 @@ __global__ void __launch_bounds__(1024) k_fin_count(Workspace W) {
   }
   if (threadIdx.x == 0) { mb.ncmd = cmd_run; mb.nlit = lit_run; }
 }
-__global__ void __launch_bounds__(64) k_fin_write(Workspace W) {
-  uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= W.num_units) return;
+__global__ void __launch_bounds__(PARSE_WARPS * 32) k_fin_write(Workspace W) {
+  uint32_t u = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);
+  if (u >= W.num_units || (threadIdx.x & 31) != 0) return;
   const uint32_t m = u / W.P.mb_units;
   const MBDesc& mb = W.mb[m];
   const UnitView V = unit_view(W);
@@ -718,25 +724,63 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split_greedy(Workspace W) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Header: one thread per metablock builds all prefix codes and the metablock header bits.
+// Header.  k_trees: one warp (lane 0) per prefix code of a metablock -- count smoothing, length-limited Huffman
+// tree, canonical codes, serialised code description into a private slot.  k_header: one warp per metablock writes
+// the metablock prologue (block-split codes, context maps) and splices the per-tree descriptions behind it.
 // ---------------------------------------------------------------------------------------------------
+#define TREE_SLOT_BYTES 1536
+__global__ void __launch_bounds__(32) k_trees(Workspace W) {
+  const uint32_t m = blockIdx.y;
+  if (threadIdx.x != 0) return;
+  const MBDesc& mb = W.mb[m];
+  const EncParams& P = W.P;
+  const uint32_t nctx = ctxmap_num_contexts(mb.ctx_map_id);
+  const uint32_t* cnt = W.split_counts + (size_t)m * 6;
+  const uint32_t nlit = cnt[1] * nctx, ncmd = cnt[3], ndist = cnt[5];
+  uint32_t t = blockIdx.x;
+  if (t >= nlit + ncmd + ndist) return;
+  const uint32_t slot = t;
+  uint32_t* hist; uint8_t* depth; uint16_t* code; uint32_t A;
+  if (t < nlit) {
+    A = 256; hist = W.lit_hist + ((size_t)m * (W.max_lit_trees + 13) + t) * 256;
+    depth = W.lit_depth + ((size_t)m * W.max_lit_trees + t) * 256; code = W.lit_code + ((size_t)m * W.max_lit_trees + t) * 256;
+  } else if (t < nlit + ncmd) {
+    t -= nlit; A = 704; hist = W.cmd_hist + ((size_t)m * (W.max_cmd_types + 1) + t) * 704;
+    depth = W.cmd_depth + ((size_t)m * W.max_cmd_types + t) * 704; code = W.cmd_code + ((size_t)m * W.max_cmd_types + t) * 704;
+  } else {
+    t -= nlit + ncmd; A = 64; hist = W.dist_hist + ((size_t)m * (W.max_dist_types + 1) + t) * 64;
+    depth = W.dist_depth + ((size_t)m * W.max_dist_types + t) * 64; code = W.dist_code + ((size_t)m * W.max_dist_types + t) * 64;
+  }
+  const uint32_t tree_cap = W.max_lit_trees + W.max_cmd_types + W.max_dist_types;
+  HuffStoreWs* ws = W.tree_ws + (size_t)m * tree_cap + slot;
+  if (P.use_rle_opt) huff_optimize_counts_for_rle(A, hist, ws->rle);
+  BitWriter bw;
+  bw.init(W.tree_bits + ((size_t)m * tree_cap + slot) * TREE_SLOT_BYTES);
+  huff_build_and_store(bw, hist, A, A, ws, depth, code);
+  bw.flush_partial();
+  W.tree_nbits[(size_t)m * tree_cap + slot] = (uint32_t)bw.bit_pos();
+}
+
+__device__ __forceinline__ void append_bits(BitWriter& bw, const uint8_t* src, uint32_t nbits) {
+  uint32_t i = 0;
+  for (; i + 32 <= nbits; i += 32) {
+    uint32_t v = (uint32_t)src[i >> 3] | ((uint32_t)src[(i >> 3) + 1] << 8) | ((uint32_t)src[(i >> 3) + 2] << 16) |
+                 ((uint32_t)src[(i >> 3) + 3] << 24);
+    bw.put(32, v);
+  }
+  for (; i < nbits; i += 8) {
+    uint32_t n = nbits - i < 8 ? nbits - i : 8;
+    bw.put(n, src[i >> 3] & ((1u << n) - 1u));
+  }
+}
+
 __global__ void __launch_bounds__(32) k_header(Workspace W) {
   const uint32_t m = blockIdx.x;
   if (threadIdx.x != 0) return;
   MBDesc& mb = W.mb[m];
-  const EncParams& P = W.P;
   const uint32_t nctx = ctxmap_num_contexts(mb.ctx_map_id);
   HuffStoreWs* ws = W.huff_ws + m;
   SplitView lv = make_view(W, m, 0), cv = make_view(W, m, 1), dv = make_view(W, m, 2);
-  uint32_t* lh = W.lit_hist + (size_t)m * (W.max_lit_trees + 13) * 256;
-  uint32_t* ch = W.cmd_hist + (size_t)m * (W.max_cmd_types + 1) * 704;
-  uint32_t* dh = W.dist_hist + (size_t)m * (W.max_dist_types + 1) * 64;
-  if (P.use_rle_opt) {
-    uint8_t* good = ws->rle;
-    for (uint32_t t = 0; t < lv.num_types * nctx; ++t) huff_optimize_counts_for_rle(256, lh + (size_t)t * 256, good);
-    for (uint32_t t = 0; t < cv.num_types; ++t) huff_optimize_counts_for_rle(704, ch + (size_t)t * 704, good);
-    for (uint32_t t = 0; t < dv.num_types; ++t) huff_optimize_counts_for_rle(64, dh + (size_t)t * 64, good);
-  }
   BitWriter bw;
   bw.init(W.hdr + (size_t)m * W.hdr_cap);
   store_compressed_metablock_header(bw, false, mb.len);
@@ -750,12 +794,10 @@ __global__ void __launch_bounds__(32) k_header(Workspace W) {
   if (mb.ctx_map_id == CTXMAP_NONE) store_trivial_context_map(bw, lv.num_types, 6, ws);
   else store_static_literal_context_map(bw, lv.num_types, mb.ctx_map_id, W.ctxmap_ws + (size_t)m * 256 * 64, ws);
   store_trivial_context_map(bw, dv.num_types, 2, ws);
-  uint8_t* ld = W.lit_depth + (size_t)m * W.max_lit_trees * 256; uint16_t* lc = W.lit_code + (size_t)m * W.max_lit_trees * 256;
-  uint8_t* cd = W.cmd_depth + (size_t)m * W.max_cmd_types * 704; uint16_t* cc = W.cmd_code + (size_t)m * W.max_cmd_types * 704;
-  uint8_t* dd = W.dist_depth + (size_t)m * W.max_dist_types * 64; uint16_t* dcode = W.dist_code + (size_t)m * W.max_dist_types * 64;
-  for (uint32_t t = 0; t < lv.num_types * nctx; ++t) huff_build_and_store(bw, lh + (size_t)t * 256, 256, 256, ws, ld + (size_t)t * 256, lc + (size_t)t * 256);
-  for (uint32_t t = 0; t < cv.num_types; ++t) huff_build_and_store(bw, ch + (size_t)t * 704, 704, 704, ws, cd + (size_t)t * 704, cc + (size_t)t * 704);
-  for (uint32_t t = 0; t < dv.num_types; ++t) huff_build_and_store(bw, dh + (size_t)t * 64, 64, 64, ws, dd + (size_t)t * 64, dcode + (size_t)t * 64);
+  const uint32_t tree_cap = W.max_lit_trees + W.max_cmd_types + W.max_dist_types;
+  const uint32_t ntrees = lv.num_types * nctx + cv.num_types + dv.num_types;
+  for (uint32_t t = 0; t < ntrees; ++t)
+    append_bits(bw, W.tree_bits + ((size_t)m * tree_cap + t) * TREE_SLOT_BYTES, W.tree_nbits[(size_t)m * tree_cap + t]);
   bw.flush_partial();
   mb.hdr_bits = (uint32_t)bw.bit_pos();
 }
