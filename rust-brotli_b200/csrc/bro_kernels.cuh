@@ -381,17 +381,200 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
 // Parse: one thread per unit.
 // ---------------------------------------------------------------------------------------------------
 #define PARSE_WARPS 4
+
+// unaligned little-endian loads built from aligned words (the input has >= 512 readable bytes of padding)
+__device__ __forceinline__ uint32_t ldu32(const uint8_t* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+  uint32_t w0 = q[0];
+  if (sh == 0) return w0;
+  return __funnelshift_r(w0, q[1], sh);
+}
+__device__ __forceinline__ uint64_t ldu64(const uint8_t* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+  uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+  uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+  return ((uint64_t)hi << 32) | lo;
+}
+// exact common-prefix length of cur[..] and (cur - back)[..], known to be >= start, capped at max_len (whole warp)
+__device__ __forceinline__ uint32_t warp_lcp_ext(const uint8_t* cur, uint32_t back, uint32_t start, uint32_t max_len) {
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t off = start; off < max_len; off += 128) {
+    const uint32_t o = off + 4 * lane;
+    const bool in = o < max_len;
+    uint32_t nbytes = 0;
+    if (in) {
+      uint32_t x = ldu32(cur + o) ^ ldu32(cur - back + o);
+      nbytes = x ? ((uint32_t)(__ffs((int)x) - 1) >> 3) : 4u;
+      nbytes = bmin(nbytes, max_len - o);
+    }
+    const bool full = in && nbytes == 4 && (o + 4 <= max_len);
+    const uint32_t stop = __ballot_sync(0xffffffffu, !full);
+    if (stop) {
+      const int first = __ffs((int)stop) - 1;
+      const uint32_t nb = __shfl_sync(0xffffffffu, nbytes, first);
+      return bmin(off + 4u * (uint32_t)first + nb, max_len);
+    }
+  }
+  return max_len;
+}
+
+// Warp-cooperative form of parse_unit (bro_parse.cuh): identical results, but the last-distance probes of a window
+// of G = 32 / NL consecutive positions are issued by all lanes at once (lane = position * NL + candidate) and the
+// serial greedy / lazy decisions are then folded from registers with shuffles.  All scalar state is warp-uniform.
+template <int NL>
+__device__ __forceinline__ uint32_t parse_unit_warp(const EncParams& P, const uint8_t* data, const uint32_t* best,
+                                                    uint32_t ustart, uint32_t uend, RawCmd* out, uint32_t* tail,
+                                                    uint32_t* ncopy) {
+  constexpr int G = 32 / NL;
+  constexpr uint32_t CAPA = 8;  // bytes compared per probe in the parallel phase
+  const uint32_t FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t j_lane = lane / NL, i_lane = lane % NL;
+  int32_t dc[4] = {0x3fffffff, 0x3fffffff, 0x3fffffff, 0x3fffffff};
+  const uint32_t htl = P.hash_type == 6 ? 8u : 4u;
+  const uint32_t window = P.quality < 9 ? 64u : 512u;
+  const int n_last = P.n_last;
+  uint32_t pos = ustart, insert_len = 0, ncmd = 0, copied = 0;
+  uint32_t arh = pos + window;
+  bool have_m = false;
+  Match m;
+  m.len = m.dist = m.score = 0;
+  int delayed = 0;
+
+  auto max_backward_at = [&](uint32_t p) -> uint32_t {
+    return (P.abs_base >= P.max_backward) ? P.max_backward : bmin(p + P.abs_base, P.max_backward);
+  };
+
+  while (have_m || pos + htl < uend) {
+    // ---------------- phase A: parallel probes for positions wbase .. wbase + G - 1 ----------------
+    const uint32_t wbase = pos;
+    uint32_t mylen = 0;
+    bool myvalid = false;
+    {
+      const uint32_t p = wbase + j_lane;
+      if ((int)i_lane < n_last && p < uend) {
+        const int32_t back = cache_candidate(dc, (int)i_lane);
+        if (back > 0 && (uint32_t)back <= max_backward_at(p)) {
+          myvalid = true;
+          const uint64_t x = ldu64(data + p) ^ ldu64(data + p - back);
+          mylen = x ? ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : CAPA;
+          mylen = bmin(mylen, uend - p);
+        }
+      }
+    }
+    uint32_t mybest = 0;
+    if (lane < (uint32_t)G && wbase + lane < uend) mybest = best[wbase + lane];
+
+    // fold of one position of the window == find_match() of bro_parse.cuh
+    auto fold = [&](int j, uint32_t max_len, Match* o) -> bool {
+      const uint32_t p = wbase + (uint32_t)j;
+      uint32_t best_score = BRO_MIN_SCORE, best_len = 0, best_dist = 0;
+      bool found = false;
+      for (int i = 0; i < n_last; ++i) {
+        const int src = j * NL + i;
+        const bool v = __shfl_sync(FULL, (int)myvalid, src) != 0;
+        uint32_t len = __shfl_sync(FULL, mylen, src);
+        if (!v) continue;
+        const uint32_t back = (uint32_t)cache_candidate(dc, i);
+        len = bmin(len, max_len);
+        if (len == CAPA && max_len > CAPA) len = warp_lcp_ext(data + p, back, CAPA, max_len);
+        if (best_len < max_len && len <= best_len) continue;
+        if (len >= 3 || (len == 2 && i < 2)) {
+          const uint32_t score = score_last_distance(P.hash_type, len, (uint32_t)i);
+          if (best_score < score) { best_score = score; best_len = len; best_dist = back; found = true; }
+        }
+      }
+      const uint32_t b = __shfl_sync(FULL, mybest, j);
+      const uint32_t blen = b & 0xFFu;
+      if (blen != 0) {
+        const uint32_t bdist = b >> 8;
+        uint32_t len = bmin(blen, max_len);
+        if (blen >= P.lcap && max_len > len) len = warp_lcp_ext(data + p, bdist, len, max_len);
+        if (len >= 4) {
+          const uint32_t score = score_regular(P.hash_type, len, bdist);
+          if (best_score < score) { best_score = score; best_len = len; best_dist = bdist; found = true; }
+        }
+      }
+      o->len = best_len; o->dist = best_dist; o->score = best_score;
+      return found;
+    };
+
+    // ---------------- phase B: serial decisions over the window (warp-uniform) ----------------
+    int j = 0;
+    for (;;) {
+      if (!have_m) {
+        if (!(pos + htl < uend) || j >= G) break;
+        if (fold(j, uend - pos, &m)) {
+          have_m = true;
+          delayed = 0;
+        } else {
+          insert_len++;
+          pos++;
+          j++;
+          if (pos > arh) {
+            const uint32_t margin = bmax(htl - 1u, 4u);
+            if (pos + 16 + margin >= uend) { insert_len += uend - pos; pos = uend; }
+            else if (pos > arh + 4 * window) { insert_len += 16; pos += 16; }
+            else { insert_len += 8; pos += 8; }
+            break;  // jumped: new window
+          }
+          continue;
+        }
+      }
+      // a match m is pending at pos: lazy evaluation of pos + 1
+      if (j + 1 >= G) break;  // pos + 1 is outside this window: re-probe with the window starting at pos
+      {
+        Match m2;
+        const bool f2 = fold(j + 1, uend - pos - 1, &m2);
+        if (f2 && m2.score >= m.score + 175u) {
+          pos++;
+          insert_len++;
+          j++;
+          m = m2;
+          if (++delayed < 4 && pos + htl < uend) continue;
+        }
+      }
+      // accept m at pos
+      arh = pos + 2 * m.len + window;
+      if ((int32_t)m.dist != dc[0]) { dc[3] = dc[2]; dc[2] = dc[1]; dc[1] = dc[0]; dc[0] = (int32_t)m.dist; }
+      if (lane == 0) {
+        out[ncmd].insert_len = insert_len;
+        out[ncmd].copy_len = m.len;
+        out[ncmd].distance = m.dist;
+      }
+      ++ncmd;
+      insert_len = 0;
+      copied += m.len;
+      pos += m.len;
+      have_m = false;
+      break;  // the distance cache changed: new window
+    }
+  }
+  insert_len += uend - pos;
+  *tail = insert_len;
+  *ncopy = copied;
+  return ncmd;
+}
+
 __global__ void __launch_bounds__(PARSE_WARPS * 32) k_parse(Workspace W) {
-  // One parse unit per WARP: units follow unrelated control flow, so putting 32 of them in one warp serialises
-  // them (measured 8.9 ms -> see profiles/); lane 0 walks the unit.
-  uint32_t u = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);
-  if (u >= W.num_units || (threadIdx.x & 31) != 0) return;
+  // One parse unit per warp.
+  const uint32_t u = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);
+  if (u >= W.num_units) return;
   const EncParams& P = W.P;
-  uint32_t s = u * P.unit, e = bmin(P.n, s + P.unit), tail, ncopy;
+  const uint32_t s = u * P.unit, e = bmin(P.n, s + P.unit);
+  uint32_t tail, ncopy, ncmd;
   const uint32_t cu = P.unit / 2 + 1;
-  W.unit_ncmd[u] = parse_unit(P, W.data, W.best, s, e, W.raw + (size_t)u * cu, &tail, &ncopy);
-  W.unit_tail[u] = tail;
-  W.unit_ncopy[u] = ncopy;
+  if (P.n_last <= 4) ncmd = parse_unit_warp<4>(P, W.data, W.best, s, e, W.raw + (size_t)u * cu, &tail, &ncopy);
+  else ncmd = parse_unit_warp<16>(P, W.data, W.best, s, e, W.raw + (size_t)u * cu, &tail, &ncopy);
+  if ((threadIdx.x & 31) == 0) {
+    W.unit_ncmd[u] = ncmd;
+    W.unit_tail[u] = tail;
+    W.unit_ncopy[u] = ncopy;
+  }
 }
 
 __device__ __forceinline__ UnitView unit_view(const Workspace& W) {
