@@ -54,28 +54,28 @@ BRO_HD uint64_t xlog2x_q16(const uint32_t* lut, uint32_t x) { return (uint64_t)x
 // RFC 7932 constants
 // ---------------------------------------------------------------------------------------------------
 BRO_HD uint32_t ins_base(uint32_t code) {
-  const uint32_t t[24] = {0, 1, 2, 3, 4, 5, 6, 8, 10, 14, 18, 26, 34, 50, 66, 98, 130, 194, 322, 578, 1090, 2114, 6210, 22594};
+  static constexpr uint32_t t[24] = {0, 1, 2, 3, 4, 5, 6, 8, 10, 14, 18, 26, 34, 50, 66, 98, 130, 194, 322, 578, 1090, 2114, 6210, 22594};
   return t[code];
 }
 BRO_HD uint32_t ins_extra(uint32_t code) {
-  const uint8_t t[24] = {0, 0, 0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 7, 8, 9, 10, 12, 14, 24};
+  static constexpr uint8_t t[24] = {0, 0, 0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 7, 8, 9, 10, 12, 14, 24};
   return t[code];
 }
 BRO_HD uint32_t copy_base(uint32_t code) {
-  const uint32_t t[24] = {2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 18, 22, 30, 38, 54, 70, 102, 134, 198, 326, 582, 1094, 2118};
+  static constexpr uint32_t t[24] = {2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 18, 22, 30, 38, 54, 70, 102, 134, 198, 326, 582, 1094, 2118};
   return t[code];
 }
 BRO_HD uint32_t copy_extra(uint32_t code) {
-  const uint8_t t[24] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 7, 8, 9, 10, 24};
+  static constexpr uint8_t t[24] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 7, 8, 9, 10, 24};
   return t[code];
 }
 BRO_HD uint32_t blocklen_offset(uint32_t code) {
-  const uint32_t t[26] = {1, 5, 9, 13, 17, 25, 33, 41, 49, 65, 81, 97, 113, 145, 177, 209,
+  static constexpr uint32_t t[26] = {1, 5, 9, 13, 17, 25, 33, 41, 49, 65, 81, 97, 113, 145, 177, 209,
                           241, 305, 369, 497, 753, 1265, 2289, 4337, 8433, 16625};
   return t[code];
 }
 BRO_HD uint32_t blocklen_nbits(uint32_t code) {
-  const uint8_t t[26] = {2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 6, 6, 7, 8, 9, 10, 11, 12, 13, 24};
+  static constexpr uint8_t t[26] = {2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 6, 6, 7, 8, 9, 10, 11, 12, 13, 24};
   return t[code];
 }
 BRO_HD uint32_t blocklen_prefix_code(uint32_t len) {  // brotli_bit_stream.rs:1370-1388
@@ -86,7 +86,7 @@ BRO_HD uint32_t blocklen_prefix_code(uint32_t len) {  // brotli_bit_stream.rs:13
 
 // UTF8 literal context (RFC 7932 7.1).  lut0 is indexed by the previous byte, lut1 by the one before.
 BRO_HD uint8_t utf8_lut0(uint32_t c) {
-  const uint8_t ascii0[128] = {
+  static constexpr uint8_t ascii0[128] = {
       0,  0,  0,  0,  0,  0,  0,  0,  0,  4,  4,  0,  0,  4,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,
       0,  0,  0,  0,  0,  0,  8,  12, 16, 12, 12, 20, 12, 16, 24, 28, 12, 12, 32, 12, 36, 12, 44, 44, 44, 44,
       44, 44, 44, 44, 44, 44, 32, 32, 24, 40, 28, 12, 12, 48, 52, 52, 52, 48, 52, 52, 52, 48, 52, 52, 52, 52,
@@ -114,7 +114,7 @@ BRO_HD uint32_t context_utf8(uint8_t p1, uint8_t p2) { return utf8_lut0(p1) | ut
 enum { CTXMAP_NONE = 0, CTXMAP_SIMPLE2 = 1, CTXMAP_CONT3 = 2, CTXMAP_COMPLEX13 = 3 };
 BRO_HD uint32_t ctxmap_num_contexts(int id) { return id == 0 ? 1u : id == 1 ? 2u : id == 2 ? 3u : 13u; }
 BRO_HD uint32_t ctxmap_lookup(int id, uint32_t ctx6) {
-  const uint8_t complex13[64] = {11, 11, 12, 12, 0, 0, 0, 0, 1, 1, 9, 9, 2, 2, 2, 2, 1, 1, 1, 1, 8, 3,
+  static constexpr uint8_t complex13[64] = {11, 11, 12, 12, 0, 0, 0, 0, 1, 1, 9, 9, 2, 2, 2, 2, 1, 1, 1, 1, 8, 3,
                                  3,  3,  1,  1,  1, 1, 2, 2, 2, 2, 8, 4, 4, 4, 8, 7, 4, 4, 8, 0, 0, 0,
                                  3,  3,  3,  3,  5, 5, 10, 5, 5, 5, 10, 5, 6, 6, 6, 6, 6, 6, 6, 6};
   if (id == CTXMAP_NONE) return 0;

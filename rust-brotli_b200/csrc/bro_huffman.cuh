@@ -42,7 +42,7 @@ BRO_HD_NOINLINE bool huff_set_depth(int p0, HuffNode* pool, uint8_t* depth, int 
 }
 
 BRO_HD_NOINLINE void huff_sort(HuffNode* items, uint32_t n) {
-  const uint32_t gaps[6] = {132, 57, 23, 10, 4, 1};
+  static constexpr uint32_t gaps[6] = {132, 57, 23, 10, 4, 1};
   if (n < 13) {
     for (uint32_t i = 1; i < n; ++i) {
       HuffNode tmp = items[i];
@@ -300,9 +300,9 @@ BRO_HD_NOINLINE void huff_store_complex(BitWriter& bw, const uint8_t* depths, ui
   huff_create_tree(histogram, 18, 5, ws->nodes, cl_depth);
   huff_depths_to_codes(cl_depth, 18, cl_bits);
   {  // brotli_bit_stream.rs:764-808
-    const uint8_t kStorageOrder[18] = {1, 2, 3, 4, 0, 5, 17, 6, 16, 7, 8, 9, 10, 11, 12, 13, 14, 15};
-    const uint8_t kSymbols[6] = {0, 7, 3, 2, 1, 15};
-    const uint8_t kLengths[6] = {2, 4, 3, 2, 2, 4};
+    static constexpr uint8_t kStorageOrder[18] = {1, 2, 3, 4, 0, 5, 17, 6, 16, 7, 8, 9, 10, 11, 12, 13, 14, 15};
+    static constexpr uint8_t kSymbols[6] = {0, 7, 3, 2, 1, 15};
+    static constexpr uint8_t kLengths[6] = {2, 4, 3, 2, 2, 4};
     uint32_t skip_some = 0, codes_to_store = 18;
     if (num_codes > 1)
       for (; codes_to_store > 0; --codes_to_store)

@@ -37,8 +37,10 @@ BRO_HD uint32_t score_regular(int hash_type, uint32_t len, uint32_t backward) {
 }
 BRO_HD uint32_t score_last_distance(int hash_type, uint32_t len, uint32_t i) {
   if (hash_type == 9) {
-    const uint16_t cost[16] = {7740, 7585, 7563, 7553, 7587, 7587, 7584, 7584, 7581, 7581, 7575, 7575, 7565, 7565, 7555, 7555};
-    return (540u * len + cost[i]) >> 2;
+    // kDistanceShortCodeCost (mod.rs:664-683) = 7553 + {187,32,10,0,34,34,31,31 | 28,28,22,22,12,12,2,2}, one byte each
+    const uint64_t lo = 0x1F1F2222000A20BBull, hi = 0x02020C0C16161C1Cull;
+    const uint32_t delta = (uint32_t)(((i < 8 ? lo : hi) >> ((i & 7u) * 8u)) & 0xFFu);
+    return (540u * len + 7553u + delta) >> 2;
   }
   uint32_t s = 135u * len + 1935u;
   if (i != 0) s -= 39u + ((0x1ca10u >> (i & 0xe)) & 0xe);
@@ -73,9 +75,14 @@ struct Match {
 
 // candidate i of the (expanded) distance cache: mod.rs:632-655
 BRO_HD int32_t cache_candidate(const int32_t* dc, int i) {
-  const int8_t idx[16] = {0, 1, 2, 3, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1};
-  const int8_t off[16] = {0, 0, 0, 0, -1, 1, -2, 2, -3, 3, -1, 1, -2, 2, -3, 3};
-  return dc[idx[i]] + off[i];
+  // i: 0..3 -> dc[i]; 4..9 -> dc[0] -1,+1,-2,+2,-3,+3; 10..15 -> dc[1] -1,+1,...   (pure arithmetic: no lookup
+  // table, so dc[] stays in registers on the device)
+  if (i < 4) return i == 0 ? dc[0] : (i == 1 ? dc[1] : (i == 2 ? dc[2] : dc[3]));
+  uint32_t k = (uint32_t)i - 4u;
+  uint32_t base = (uint32_t)dc[0];
+  if (k >= 6u) { k -= 6u; base = (uint32_t)dc[1]; }
+  const uint32_t mag = (k >> 1) + 1u;
+  return (int32_t)((k & 1u) ? base + mag : base - mag);  // unsigned on purpose: no signed-overflow assumptions
 }
 
 // Best match at pos: last-distance probes (serial state) combined with the precomputed bucket candidate.

@@ -104,7 +104,7 @@ BRO_HD void ctx_sample_stride(const uint8_t* d, uint32_t sp, CtxSampleHist* h, b
       prev1 = lit;
     }
   }
-  const uint8_t lut4[4] = {0, 0, 1, 2};
+  static constexpr uint8_t lut4[4] = {0, 0, 1, 2};
   uint32_t prev = lut4[d[sp] >> 6] * 3u;
   for (uint32_t pos = sp + 1; pos < sp + 64; ++pos) {
     uint8_t lit = d[pos];

@@ -17,7 +17,7 @@ def build_model(force=False):
     srcs = [os.path.join(_HERE, "gpu_model.cpp")] + [os.path.join(_ROOT, "rust-brotli_b200", "csrc", f) for f in
             ("bro_common.cuh", "bro_huffman.cuh", "bro_meta.cuh", "bro_parse.cuh", "bro_split.cuh")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-w", "-I",
+        subprocess.check_call(["g++", "-O2", "-fwrapv", "-std=c++17", "-shared", "-fPIC", "-w", "-I",
                                os.path.join(_ROOT, "rust-brotli_b200", "csrc"), srcs[0], "-o", so])
     return so
 
