@@ -157,7 +157,7 @@ struct B200Encoder {
     W->hdr_cap = P.split ? (384u << 10) : (16u << 10);
     if (!d_best.ensure(((size_t)c + 64) * 4)) return false;
     if (!d_raw.ensure((size_t)NU * cu * sizeof(RawCmd))) return false;
-    if (!d_unit.ensure((size_t)NU * 6 * 4)) return false;
+    if (!d_unit.ensure((size_t)NU * 7 * 4)) return false;
     if (!d_cmds.ensure((size_t)NM * cmd_cap * sizeof(GCmd))) return false;
     if (!d_cmd_bits.ensure((size_t)NM * cmd_cap * 4)) return false;
     if (!d_lit_syms.ensure(((size_t)c + 64) * 2)) return false;
@@ -179,7 +179,6 @@ struct B200Encoder {
     if (!d_huff_ws.ensure((size_t)NM * sizeof(HuffStoreWs))) return false;
     if (!d_ctxmap_ws.ensure((size_t)NM * 256 * 64 * 4)) return false;
     const size_t tree_cap = (size_t)W->max_lit_trees + W->max_cmd_types + W->max_dist_types;
-    if (!d_tree_ws.ensure((size_t)NM * tree_cap * sizeof(HuffStoreWs))) return false;
     if (!d_tree_bits.ensure((size_t)NM * tree_cap * TREE_SLOT_BYTES)) return false;
     if (!d_tree_nbits.ensure((size_t)NM * tree_cap * 4)) return false;
     // sort scratch
@@ -195,7 +194,7 @@ struct B200Encoder {
     W->raw = d_raw.as<RawCmd>();
     uint32_t* up = d_unit.as<uint32_t>();
     W->unit_ncmd = up; W->unit_tail = up + NU; W->unit_ncopy = up + 2 * (size_t)NU;
-    W->unit_cmd_off = up + 3 * (size_t)NU; W->unit_lit_off = up + 4 * (size_t)NU; W->unit_ndist = up + 5 * (size_t)NU;
+    W->unit_cmd_off = up + 3 * (size_t)NU; W->unit_lit_off = up + 4 * (size_t)NU; W->unit_ndist = up + 5 * (size_t)NU; W->unit_dist_off = up + 6 * (size_t)NU;
     W->cmds = d_cmds.as<GCmd>();
     W->cmd_bits = d_cmd_bits.as<uint32_t>();
     W->lit_syms = d_lit_syms.as<uint16_t>();

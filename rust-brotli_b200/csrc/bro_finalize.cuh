@@ -29,7 +29,7 @@ struct GCmd {  // final command record in device memory (32 bytes)
   uint32_t lit_idx;   // rank of its first literal among the metablock's literals
   uint32_t dist_idx;  // rank of its distance symbol among the metablock's distance symbols
   uint32_t pos;       // input position of its first literal
-  uint32_t pad;
+  uint32_t pad;       // owning parse unit (device: dist_idx is unit-relative until unit_dist_off[pad] is added)
   BRO_HD Cmd as_cmd() const {
     Cmd c;
     c.insert_len = insert_len; c.copy_len = copy_len; c.dist_extra = dist_extra;
@@ -128,7 +128,7 @@ BRO_HD_NOINLINE uint32_t finalize_unit(const UnitView& V, uint32_t u0, uint32_t 
     g.lit_idx = lit_idx - ((i == 0) ? carry : 0u);
     g.dist_idx = ndist;
     g.pos = pos - ((i == 0) ? carry : 0u);
-    g.pad = 0;
+    g.pad = u;  // owning unit: consumers add the unit's distance-symbol prefix to dist_idx
     if (g.cmd_prefix >= 128) ++ndist;
     out[nout++] = g;
     lit_idx += rc[i].insert_len;
@@ -147,7 +147,7 @@ BRO_HD_NOINLINE uint32_t finalize_unit(const UnitView& V, uint32_t u0, uint32_t 
       g.lit_idx = lit_idx + V.tail[u] - carry_out;
       g.dist_idx = ndist;
       g.pos = uend - carry_out;
-      g.pad = 0;
+      g.pad = u;
       out[nout++] = g;
     }
   }

@@ -60,7 +60,7 @@ struct Workspace {
   // parse
   RawCmd* raw;
   uint32_t *unit_ncmd, *unit_tail, *unit_ncopy;
-  uint32_t *unit_cmd_off, *unit_lit_off, *unit_ndist;  // metablock-relative
+  uint32_t *unit_cmd_off, *unit_lit_off, *unit_ndist, *unit_dist_off;  // metablock-relative
   // commands
   GCmd* cmds;           // [num_mb][cmd_cap]
   uint32_t cmd_cap;     // per metablock
@@ -281,6 +281,23 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(SortArgs a) {
   }
 }
 
+// unaligned little-endian loads built from aligned words (the input has >= 512 readable bytes of padding)
+__device__ __forceinline__ uint32_t ldu32(const uint8_t* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+  uint32_t w0 = q[0];
+  if (sh == 0) return w0;
+  return __funnelshift_r(w0, q[1], sh);
+}
+__device__ __forceinline__ uint64_t ldu64(const uint8_t* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+  uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+  uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+  return ((uint64_t)hi << 32) | lo;
+}
 // ---------------------------------------------------------------------------------------------------
 // Match search over the sorted position list of one batch.
 // ---------------------------------------------------------------------------------------------------
@@ -340,16 +357,25 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
     const uint32_t key = s_key[i];
     const uint32_t max_backward = bmin(p, a.max_backward);
     const uint32_t m0 = s_d0[i], m1 = s_d1[i], m2 = s_d2[i], m3 = s_d3[i];
-    for (uint32_t c = 1; c <= (uint32_t)a.depth; ++c) {
-      const uint32_t ci = i - c;
-      if (s_key[ci] != key) break;
-      const uint32_t backward = prel - s_pos[ci];
-      if (backward > max_backward) break;
-      uint32_t x = s_d0[ci] ^ m0;
-      uint32_t len;
-      if (x) len = (uint32_t)(__ffs((int)x) - 1) >> 3;
-      else {
-        x = s_d1[ci] ^ m1;
+    bool done = false;
+    for (uint32_t cbase = 0; cbase < (uint32_t)a.depth && !done; cbase += 16) {
+      // phase 1 (branch-free, unrolled): which of the next 16 older entries share the bucket key and the first 4 bytes
+      uint32_t mask = 0;
+#pragma unroll
+      for (uint32_t c = 0; c < 16; ++c) {
+        const uint32_t ci = i - 1u - cbase - c;
+        mask |= (uint32_t)((s_key[ci] == key) & (s_d0[ci] == m0)) << c;
+      }
+      if (s_key[i - 16u - cbase] != key) done = true;  // the bucket ends inside this group: nothing older can match
+      // phase 2: full evaluation of the survivors, nearest first
+      while (mask) {
+        const uint32_t c = (uint32_t)__ffs((int)mask) - 1u;
+        mask &= mask - 1u;
+        const uint32_t ci = i - 1u - cbase - c;
+        const uint32_t backward = prel - s_pos[ci];
+        if (backward > max_backward) { done = true; break; }
+        uint32_t len;
+        uint32_t x = s_d1[ci] ^ m1;
         if (x) len = 4 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
         else {
           x = s_d2[ci] ^ m2;
@@ -361,16 +387,19 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
               len = 16;
               const uint8_t* pa = a.data + p;
               const uint8_t* pb = pa - backward;
-              while (len < maxl && pa[len] == pb[len]) ++len;
+              while (len + 8 <= maxl) {
+                const uint64_t y = ldu64(pa + len) ^ ldu64(pb + len);
+                if (y) { len += (uint32_t)(__ffsll((long long)y) - 1) >> 3; break; }
+                len += 8;
+              }
+              if (len + 8 > maxl) while (len < maxl && pa[len] == pb[len]) ++len;
             }
           }
         }
-      }
-      if (len > maxl) len = maxl;
-      if (len >= 4) {
-        uint32_t score = score_regular(a.hash_type, len, backward);
+        if (len > maxl) len = maxl;
+        const uint32_t score = score_regular(a.hash_type, len, backward);
         if (score > best_score) { best_score = score; best_len = len; best_dist = backward; }
-        if (len == maxl) break;
+        if (len == maxl) { done = true; break; }
       }
     }
   }
@@ -382,23 +411,6 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
 // ---------------------------------------------------------------------------------------------------
 #define PARSE_WARPS 4
 
-// unaligned little-endian loads built from aligned words (the input has >= 512 readable bytes of padding)
-__device__ __forceinline__ uint32_t ldu32(const uint8_t* p) {
-  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-  const uint32_t sh = (uint32_t)(a & 3u) * 8u;
-  uint32_t w0 = q[0];
-  if (sh == 0) return w0;
-  return __funnelshift_r(w0, q[1], sh);
-}
-__device__ __forceinline__ uint64_t ldu64(const uint8_t* p) {
-  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-  const uint32_t sh = (uint32_t)(a & 3u) * 8u;
-  uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
-  uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-  return ((uint64_t)hi << 32) | lo;
-}
 // exact common-prefix length of cur[..] and (cur - back)[..], known to be >= start, capped at max_len (whole warp)
 __device__ __forceinline__ uint32_t warp_lcp_ext(const uint8_t* cur, uint32_t back, uint32_t start, uint32_t max_len) {
   const uint32_t lane = threadIdx.x & 31;
@@ -560,6 +572,163 @@ __device__ __forceinline__ uint32_t parse_unit_warp(const EncParams& P, const ui
   return ncmd;
 }
 
+// lane-local exact common-prefix length (>= start), used for the rare candidates that match the whole probe width
+__device__ __forceinline__ uint32_t lane_lcp_ext(const uint8_t* cur, uint32_t back, uint32_t start, uint32_t max_len) {
+  while (start + 8 <= max_len) {
+    const uint64_t x = ldu64(cur + start) ^ ldu64(cur - back + start);
+    if (x) return start + ((uint32_t)(__ffsll((long long)x) - 1) >> 3);
+    start += 8;
+  }
+  while (start < max_len && cur[start] == (cur - back)[start]) ++start;
+  return start;
+}
+
+// Fast path for n_last == 4 with the H5/H6 scores (q5, q6).  With penalties 0,39,43,43 (non-decreasing) the sequential
+// candidate fold of find_match() is exactly "highest score, ties to the lower cache index", so all 8 positions of a
+// window are resolved completely in parallel (4 lanes per position, 2 shuffle-max steps) and the serial greedy / lazy
+// walk only reads finished (found, len, dist, score) tuples: ballots locate the next match, shuffles fetch it.
+__device__ __forceinline__ uint32_t parse_unit_warp4(const EncParams& P, const uint8_t* data, const uint32_t* best,
+                                                     uint32_t ustart, uint32_t uend, RawCmd* out, uint32_t* tail,
+                                                     uint32_t* ncopy) {
+  constexpr int G = 8;
+  constexpr uint32_t CAPA = 8;
+  const uint32_t FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t j_lane = lane >> 2, i_lane = lane & 3;
+  int32_t dc0 = 0x3fffffff, dc1 = 0x3fffffff, dc2 = 0x3fffffff, dc3 = 0x3fffffff;
+  const uint32_t htl = P.hash_type == 6 ? 8u : 4u;
+  const uint32_t window = 64u;  // quality < 9 on this path
+  uint32_t pos = ustart, insert_len = 0, ncmd = 0, copied = 0;
+  uint32_t arh = pos + window;
+  bool have_m = false;
+  uint32_t m_len = 0, m_dist = 0, m_score = 0;
+  int delayed = 0;
+  const bool near_start = P.abs_base < P.max_backward;
+
+  while (have_m || pos + htl < uend) {
+    // ---------------- phase A: every position of the window fully resolved, in parallel ----------------
+    const uint32_t wbase = pos;
+    const uint32_t p = wbase + j_lane;
+    const bool p_ok = p < uend;
+    const uint32_t maxl = p_ok ? uend - p : 0u;
+    uint32_t clen = 0, cdist = 0, key = 0;
+    if (p_ok) {
+      const int32_t back = i_lane == 0 ? dc0 : (i_lane == 1 ? dc1 : (i_lane == 2 ? dc2 : dc3));
+      const uint32_t mb = near_start ? bmin(p + P.abs_base, P.max_backward) : P.max_backward;
+      if (back > 0 && (uint32_t)back <= mb) {
+        const uint64_t x = ldu64(data + p) ^ ldu64(data + p - back);
+        uint32_t len = x ? ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : CAPA;
+        len = bmin(len, maxl);
+        if (len == CAPA && maxl > CAPA) len = lane_lcp_ext(data + p, (uint32_t)back, CAPA, maxl);
+        if (len >= 3 || (len == 2 && i_lane < 2)) {
+          const uint32_t score = score_last_distance(5, len, i_lane);
+          key = (score << 2) | (3u - i_lane);
+          clen = len;
+          cdist = (uint32_t)back;
+        }
+      }
+    }
+    {  // best of the 4 cache candidates of this position
+      uint32_t k = key;
+      k = max(k, __shfl_xor_sync(FULL, k, 1));
+      k = max(k, __shfl_xor_sync(FULL, k, 2));
+      const int src = (int)((lane & ~3u) + (3u - (k & 3u)));
+      const uint32_t wl = __shfl_sync(FULL, clen, src), wd = __shfl_sync(FULL, cdist, src);
+      key = k; clen = wl; cdist = wd;
+    }
+    uint32_t f_score = key ? (key >> 2) : BRO_MIN_SCORE, f_len = key ? clen : 0u, f_dist = key ? cdist : 0u;
+    bool f_found = key != 0;
+    if (p_ok && i_lane == 0) {  // bucket candidate from the match kernel must be strictly better
+      const uint32_t b = best[p];
+      const uint32_t blen = b & 0xFFu;
+      if (blen != 0) {
+        const uint32_t bdist = b >> 8;
+        uint32_t len = bmin(blen, maxl);
+        if (blen >= P.lcap && maxl > len) len = lane_lcp_ext(data + p, bdist, len, maxl);
+        if (len >= 4) {
+          const uint32_t score = score_regular(5, len, bdist);
+          if (f_score < score) { f_score = score; f_len = len; f_dist = bdist; f_found = true; }
+        }
+      }
+    }
+    // lane 4*j now holds the finished result of position wbase + j
+    const uint32_t fb = __ballot_sync(FULL, f_found && i_lane == 0);
+    uint32_t found8 = 0;  // bit j <=> a match exists at wbase + j
+#pragma unroll
+    for (int j = 0; j < G; ++j) found8 |= ((fb >> (4 * j)) & 1u) << j;
+
+    // ---------------- phase B: serial greedy / lazy walk over finished results (warp-uniform scalars) ----------------
+    int j = 0;
+    for (;;) {
+      if (!have_m) {
+        if (!(pos + htl < uend) || j >= G) break;
+        // searchable positions of this window from j on: wbase + j' + htl < uend
+        const uint32_t lim = bmin((uint32_t)G, uend - htl - wbase);  // positions j' < lim are searchable (pos + htl < uend holds)
+        const uint32_t cand = found8 & ~((1u << j) - 1u) & ((lim >= 32 ? 0xFFFFFFFFu : ((1u << lim) - 1u)));
+        const uint32_t f = cand ? (uint32_t)(__ffs((int)cand) - 1) : lim;  // first match, or end of searchable range
+        // literal steps j .. f-1, but the sparse-search heuristic may cut the run short
+        const uint32_t run = f - (uint32_t)j;
+        uint32_t steps = run;
+        bool jump = false;
+        if (run > 0 && pos + run > arh) {  // some step k (1..run) has pos + k > arh: the first such k triggers the skip
+          steps = pos > arh ? 1u : (arh - pos + 1u);
+          jump = true;
+        }
+        insert_len += steps;
+        pos += steps;
+        j += (int)steps;
+        if (jump) {
+          const uint32_t margin = bmax(htl - 1u, 4u);
+          if (pos + 16 + margin >= uend) { insert_len += uend - pos; pos = uend; }
+          else if (pos > arh + 4 * window) { insert_len += 16; pos += 16; }
+          else { insert_len += 8; pos += 8; }
+          break;
+        }
+        if (!cand || j >= G) break;  // window exhausted without a match
+        const int src = 4 * j;
+        m_len = __shfl_sync(FULL, f_len, src);
+        m_dist = __shfl_sync(FULL, f_dist, src);
+        m_score = __shfl_sync(FULL, f_score, src);
+        have_m = true;
+        delayed = 0;
+      }
+      // a match is pending at pos: lazy evaluation against pos + 1
+      if (j + 1 >= G) break;  // re-probe with the window starting at pos
+      {
+        const int src = 4 * (j + 1);
+        const bool f2 = (found8 >> (j + 1)) & 1u;
+        const uint32_t s2 = __shfl_sync(FULL, f_score, src);
+        if (f2 && s2 >= m_score + 175u) {
+          pos++;
+          insert_len++;
+          j++;
+          m_len = __shfl_sync(FULL, f_len, src);
+          m_dist = __shfl_sync(FULL, f_dist, src);
+          m_score = s2;
+          if (++delayed < 4 && pos + htl < uend) continue;
+        }
+      }
+      arh = pos + 2 * m_len + window;
+      if ((int32_t)m_dist != dc0) { dc3 = dc2; dc2 = dc1; dc1 = dc0; dc0 = (int32_t)m_dist; }
+      if (lane == 0) {
+        out[ncmd].insert_len = insert_len;
+        out[ncmd].copy_len = m_len;
+        out[ncmd].distance = m_dist;
+      }
+      ++ncmd;
+      insert_len = 0;
+      copied += m_len;
+      pos += m_len;
+      have_m = false;
+      break;
+    }
+  }
+  insert_len += uend - pos;
+  *tail = insert_len;
+  *ncopy = copied;
+  return ncmd;
+}
+
 __global__ void __launch_bounds__(PARSE_WARPS * 32) k_parse(Workspace W) {
   // One parse unit per warp.
   const uint32_t u = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);
@@ -568,7 +737,8 @@ __global__ void __launch_bounds__(PARSE_WARPS * 32) k_parse(Workspace W) {
   const uint32_t s = u * P.unit, e = bmin(P.n, s + P.unit);
   uint32_t tail, ncopy, ncmd;
   const uint32_t cu = P.unit / 2 + 1;
-  if (P.n_last <= 4) ncmd = parse_unit_warp<4>(P, W.data, W.best, s, e, W.raw + (size_t)u * cu, &tail, &ncopy);
+  if (P.n_last == 4 && P.hash_type != 9) ncmd = parse_unit_warp4(P, W.data, W.best, s, e, W.raw + (size_t)u * cu, &tail, &ncopy);
+  else if (P.n_last <= 4) ncmd = parse_unit_warp<4>(P, W.data, W.best, s, e, W.raw + (size_t)u * cu, &tail, &ncopy);
   else ncmd = parse_unit_warp<16>(P, W.data, W.best, s, e, W.raw + (size_t)u * cu, &tail, &ncopy);
   if ((threadIdx.x & 31) == 0) {
     W.unit_ncmd[u] = ncmd;
@@ -643,7 +813,9 @@ __global__ void __launch_bounds__(PARSE_WARPS * 32) k_fin_write(Workspace W) {
   const uint32_t m = u / W.P.mb_units;
   const MBDesc& mb = W.mb[m];
   const UnitView V = unit_view(W);
-  W.unit_ndist[u] = finalize_unit(V, mb.u0, mb.u1, u, W.unit_lit_off[u], W.cmds + (size_t)m * W.cmd_cap + W.unit_cmd_off[u]);
+  GCmd* dst = W.cmds + (size_t)m * W.cmd_cap + W.unit_cmd_off[u];
+  const uint32_t nd = finalize_unit(V, mb.u0, mb.u1, u, W.unit_lit_off[u], dst);
+  W.unit_ndist[u] = nd;
 }
 // One CTA per metablock: scan distance-symbol counts over units and add the prefix to each command.
 __global__ void __launch_bounds__(1024) k_fin_dist(Workspace W) {
@@ -656,12 +828,7 @@ __global__ void __launch_bounds__(1024) k_fin_dist(Workspace W) {
     uint32_t nd = u < mb.u1 ? W.unit_ndist[u] : 0;
     uint32_t tot;
     uint32_t ex = block_excl_scan_1024(nd, s_warp, &tot);
-    if (u < mb.u1) {
-      uint32_t c0 = W.unit_cmd_off[u];
-      uint32_t c1 = (u + 1 < mb.u1) ? W.unit_cmd_off[u + 1] : mb.ncmd;
-      GCmd* c = W.cmds + (size_t)m * W.cmd_cap;
-      for (uint32_t i = c0; i < c1; ++i) c[i].dist_idx += run + ex;
-    }
+    if (u < mb.u1) W.unit_dist_off[u] = run + ex;  // commands carry their unit in GCmd::pad and add this at use
     run += tot;
   }
   if (threadIdx.x == 0) mb.ndist = run;
@@ -722,7 +889,7 @@ __global__ void __launch_bounds__(256) k_symbols(Workspace W) {
   if (i >= mb.ncmd) return;
   const GCmd c = W.cmds[(size_t)m * W.cmd_cap + i];
   W.cmd_syms[(size_t)m * W.cmd_cap + i] = c.cmd_prefix;
-  if (c.copy_len != 0 && c.cmd_prefix >= 128) W.dist_syms[(size_t)m * W.cmd_cap + c.dist_idx] = c.dist_prefix & 0x3ffu;
+  if (c.copy_len != 0 && c.cmd_prefix >= 128) W.dist_syms[(size_t)m * W.cmd_cap + c.dist_idx + W.unit_dist_off[c.pad]] = c.dist_prefix & 0x3ffu;
   const uint8_t* d = W.data;
   uint16_t* ls = W.lit_syms + mb.start + c.lit_idx;
   const int id = mb.ctx_map_id;
@@ -935,7 +1102,8 @@ __global__ void __launch_bounds__(32) k_trees(Workspace W) {
     depth = W.dist_depth + ((size_t)m * W.max_dist_types + t) * 64; code = W.dist_code + ((size_t)m * W.max_dist_types + t) * 64;
   }
   const uint32_t tree_cap = W.max_lit_trees + W.max_cmd_types + W.max_dist_types;
-  HuffStoreWs* ws = W.tree_ws + (size_t)m * tree_cap + slot;
+  __shared__ HuffStoreWs ws_s;  // sort / tree scratch in shared memory: the serial tree code is latency bound
+  HuffStoreWs* ws = &ws_s;
   if (P.use_rle_opt) huff_optimize_counts_for_rle(A, hist, ws->rle);
   BitWriter bw;
   bw.init(W.tree_bits + ((size_t)m * tree_cap + slot) * TREE_SLOT_BYTES);
@@ -997,7 +1165,7 @@ __global__ void __launch_bounds__(256) k_bitlen(Workspace W) {
   const GCmd g = W.cmds[(size_t)m * W.cmd_cap + i];
   CountWriter w;
   w.bits = 0;
-  emit_command(w, mc, g.as_cmd(), i, g.lit_idx, g.dist_idx, W.data, g.pos, W.P.abs_base);
+  emit_command(w, mc, g.as_cmd(), i, g.lit_idx, g.dist_idx + W.unit_dist_off[g.pad], W.data, g.pos, W.P.abs_base);
   W.cmd_bits[(size_t)m * W.cmd_cap + i] = (uint32_t)w.bits;
 }
 // One CTA per metablock: exclusive scan of command bit lengths (in place), total -> body_bits.
@@ -1108,7 +1276,7 @@ __global__ void __launch_bounds__(256) k_emit_body(Workspace W) {
   const GCmd g = W.cmds[(size_t)m * W.cmd_cap + i];
   AtomicOrWriter w;
   w.init(W.out, mb.out_bitpos + mb.hdr_bits + W.cmd_bits[(size_t)m * W.cmd_cap + i]);
-  emit_command(w, mc, g.as_cmd(), i, g.lit_idx, g.dist_idx, W.data, g.pos, W.P.abs_base);
+  emit_command(w, mc, g.as_cmd(), i, g.lit_idx, g.dist_idx + W.unit_dist_off[g.pad], W.data, g.pos, W.P.abs_base);
   w.flush();
 }
 __global__ void __launch_bounds__(256) k_emit_raw(Workspace W) {
