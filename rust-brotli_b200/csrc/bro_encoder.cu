@@ -71,7 +71,7 @@ struct B200Encoder {
   // buffers
   DevBuf d_data, d_lut, d_sortA, d_sortB, d_hist, d_digit, d_best, d_raw, d_unit, d_cmds, d_cmd_bits, d_lit_syms,
       d_cmd_syms, d_dist_syms, d_mb, d_split_u8, d_split_u32, d_split_counts, d_hist_lit, d_hist_cmd, d_hist_dist,
-      d_split_codes, d_codes_u8, d_codes_u16, d_hdr, d_huff_ws, d_ctxmap_ws, d_out, d_total, d_tree_ws, d_tree_bits, d_tree_nbits;
+      d_split_codes, d_codes_u8, d_codes_u16, d_hdr, d_huff_ws, d_ctxmap_ws, d_out, d_total, d_tree_ws, d_tree_bits, d_tree_nbits, d_cmd_tile;
   uint8_t* h_pinned = nullptr;
   size_t h_pinned_cap = 0;
   uint64_t data_base = 0;  // absolute stream position of d_data[0]
@@ -101,7 +101,7 @@ struct B200Encoder {
     DevBuf* all[] = {&d_data, &d_lut, &d_sortA, &d_sortB, &d_hist, &d_digit, &d_best, &d_raw, &d_unit, &d_cmds, &d_cmd_bits,
                      &d_lit_syms, &d_cmd_syms, &d_dist_syms, &d_mb, &d_split_u8, &d_split_u32, &d_split_counts, &d_hist_lit,
                      &d_hist_cmd, &d_hist_dist, &d_split_codes, &d_codes_u8, &d_codes_u16, &d_hdr, &d_huff_ws, &d_ctxmap_ws,
-                     &d_out, &d_total, &d_tree_ws, &d_tree_bits, &d_tree_nbits};
+                     &d_out, &d_total, &d_tree_ws, &d_tree_bits, &d_tree_nbits, &d_cmd_tile};
     for (auto* b : all) b->release();
     if (h_pinned) cudaFreeHost(h_pinned);
     for (auto& e : ev_pool) cudaEventDestroy(e);
@@ -160,6 +160,8 @@ struct B200Encoder {
     if (!d_unit.ensure((size_t)NU * 7 * 4)) return false;
     if (!d_cmds.ensure((size_t)NM * cmd_cap * sizeof(GCmd))) return false;
     if (!d_cmd_bits.ensure((size_t)NM * cmd_cap * 4)) return false;
+    W->tile_cap = cmd_cap / 256 + 2;
+    if (!d_cmd_tile.ensure((size_t)NM * W->tile_cap * 4)) return false;
     if (!d_lit_syms.ensure(((size_t)c + 64) * 2)) return false;
     if (!d_cmd_syms.ensure((size_t)NM * cmd_cap * 2)) return false;
     if (!d_dist_syms.ensure((size_t)NM * cmd_cap * 2)) return false;
@@ -197,6 +199,7 @@ struct B200Encoder {
     W->unit_cmd_off = up + 3 * (size_t)NU; W->unit_lit_off = up + 4 * (size_t)NU; W->unit_ndist = up + 5 * (size_t)NU; W->unit_dist_off = up + 6 * (size_t)NU;
     W->cmds = d_cmds.as<GCmd>();
     W->cmd_bits = d_cmd_bits.as<uint32_t>();
+    W->cmd_tile = d_cmd_tile.as<uint32_t>();
     W->lit_syms = d_lit_syms.as<uint16_t>();
     W->cmd_syms = d_cmd_syms.as<uint16_t>();
     W->dist_syms = d_dist_syms.as<uint16_t>();

@@ -108,6 +108,9 @@ BRO_HD_NOINLINE void huff_create_tree(const uint32_t* data, uint32_t length, int
 }
 
 BRO_HD uint16_t reverse_bits(uint32_t num_bits, uint32_t bits) {
+#ifdef __CUDA_ARCH__
+  return (uint16_t)(__brev(bits) >> (32u - num_bits));
+#endif
   uint32_t r = 0;
   for (uint32_t i = 0; i < num_bits; ++i) {
     r = (r << 1) | (bits & 1u);

@@ -64,7 +64,9 @@ struct Workspace {
   // commands
   GCmd* cmds;           // [num_mb][cmd_cap]
   uint32_t cmd_cap;     // per metablock
-  uint32_t* cmd_bits;   // [num_mb][cmd_cap] bit length, then exclusive prefix
+  uint32_t* cmd_bits;   // [num_mb][cmd_cap] exclusive bit prefix inside the command's 256-tile
+  uint32_t* cmd_tile;   // [num_mb][tile_cap] tile totals, then exclusive tile offsets
+  uint32_t tile_cap;
   // symbol streams
   uint16_t* lit_syms;   // [n]  literal | ctx << 8, metablock m at m.start
   uint16_t* cmd_syms;   // [num_mb][cmd_cap]
@@ -807,15 +809,113 @@ __global__ void __launch_bounds__(1024) k_fin_count(Workspace W) {
   }
   if (threadIdx.x == 0) { mb.ncmd = cmd_run; mb.nlit = lit_run; }
 }
+// Incoming distance cache of raw command i of unit u: the last (up to) four distinct-run distances before it, looking
+// back inside the unit and, if needed, into earlier units of the metablock (same rule as finalize_unit()).
+__device__ __forceinline__ void lookback_cache(const UnitView& V, uint32_t u0, uint32_t u, uint32_t i, int32_t* dc) {
+  dc[0] = dc[1] = dc[2] = dc[3] = 0x3fffffff;
+  int k = 0;
+  uint32_t last = 0;
+  uint32_t v = u, idx = i;
+  for (;;) {
+    while (idx > 0 && k < 4) {
+      --idx;
+      const uint32_t d = V.raw[(size_t)v * V.cu + idx].distance;
+      if (d != last) { dc[k++] = (int32_t)d; last = d; }
+    }
+    if (k >= 4 || v == u0) break;
+    --v;
+    idx = V.ncmd[v];
+  }
+}
+
+// Warp-parallel form of finalize_unit(): lanes take consecutive raw commands; positions / literal ranks / distance
+// ranks come from warp scans, the distance cache from a short per-lane look-back.  Identical output.
 __global__ void __launch_bounds__(PARSE_WARPS * 32) k_fin_write(Workspace W) {
-  uint32_t u = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);
-  if (u >= W.num_units || (threadIdx.x & 31) != 0) return;
+  const uint32_t u = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);
+  if (u >= W.num_units) return;
+  const uint32_t FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x & 31;
   const uint32_t m = u / W.P.mb_units;
   const MBDesc& mb = W.mb[m];
   const UnitView V = unit_view(W);
-  GCmd* dst = W.cmds + (size_t)m * W.cmd_cap + W.unit_cmd_off[u];
-  const uint32_t nd = finalize_unit(V, mb.u0, mb.u1, u, W.unit_lit_off[u], dst);
-  W.unit_ndist[u] = nd;
+  const uint32_t u0 = mb.u0, u1 = mb.u1;
+  GCmd* out = W.cmds + (size_t)m * W.cmd_cap + W.unit_cmd_off[u];
+  const uint32_t ustart = u * V.unit;
+  const uint32_t nraw = V.ncmd[u];
+  const RawCmd* rc = V.raw + (size_t)u * V.cu;
+  const bool absorbed = unit_absorbed(V, u0, u);
+  const uint32_t carry = unit_carry_in(V, u0, u);
+  uint32_t cont = 0;  // bytes absorbed from following units by the last command
+  if (nraw) {
+    for (uint32_t v = u + 1; v < u1 && unit_absorbed(V, u0, v); ++v) {
+      cont += V.raw[(size_t)v * V.cu].copy_len;
+      if (!(V.ncmd[v] == 1 && V.tail[v] == 0)) break;
+    }
+  }
+  uint32_t lit_run = W.unit_lit_off[u], pos_run = ustart, nd_run = 0;
+  const uint32_t skip = absorbed ? 1u : 0u;
+  for (uint32_t base = 0; base < nraw; base += 32) {
+    const uint32_t i = base + lane;
+    const bool act = i < nraw;
+    uint32_t ins_r = 0, len_r = 0, dist = 0;
+    if (act) { ins_r = rc[i].insert_len; len_r = rc[i].copy_len; dist = rc[i].distance; }
+    // exclusive warp scans of literals and of covered bytes
+    uint32_t sl = ins_r, sp = ins_r + len_r;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t a1 = __shfl_up_sync(FULL, sl, o), a2 = __shfl_up_sync(FULL, sp, o);
+      if (lane >= (uint32_t)o) { sl += a1; sp += a2; }
+    }
+    const uint32_t lit_before = lit_run + sl - ins_r, pos_before = pos_run + sp - (ins_r + len_r);
+    const bool emit = act && !(i == 0 && absorbed);
+    uint32_t cmd_prefix = 0, sym_nbits = 0, extra = 0, ins = ins_r, len = len_r;
+    if (emit) {
+      if (i == 0) ins += carry;
+      if (i + 1 == nraw) len += cont;
+      int32_t dc[4];
+      lookback_cache(V, u0, u, i, dc);
+      const uint32_t code = compute_distance_code(dist, dc);
+      prefix_encode_copy_distance(code, &sym_nbits, &extra);
+      cmd_prefix = combine_length_codes(insert_length_code(ins), copy_length_code(len), code == 0);
+    }
+    const uint32_t hd = __ballot_sync(FULL, emit && cmd_prefix >= 128);
+    if (emit) {
+      GCmd g;
+      g.insert_len = ins;
+      g.copy_len = len;
+      g.dist_extra = extra;
+      g.cmd_prefix = (uint16_t)cmd_prefix;
+      g.dist_prefix = (uint16_t)sym_nbits;
+      g.lit_idx = lit_before - (i == 0 ? carry : 0u);
+      g.dist_idx = nd_run + __popc(hd & ((1u << lane) - 1u));
+      g.pos = pos_before - (i == 0 ? carry : 0u);
+      g.pad = u;
+      out[i - skip] = g;
+    }
+    lit_run += __shfl_sync(FULL, sl, 31);
+    pos_run += __shfl_sync(FULL, sp, 31);
+    nd_run += __popc(hd);
+  }
+  if (lane == 0) {
+    if (u + 1 == u1) {
+      const uint32_t carry_out = V.tail[u] + (nraw == 0 ? carry : 0u);
+      if (carry_out) {
+        const uint32_t uend = bmin(V.n, ustart + V.unit);
+        GCmd g;
+        g.insert_len = carry_out;
+        g.copy_len = 0;
+        g.dist_extra = 0;
+        g.dist_prefix = 0;
+        g.cmd_prefix = (uint16_t)combine_length_codes(insert_length_code(carry_out), copy_length_code(4), false);
+        g.lit_idx = lit_run + V.tail[u] - carry_out;
+        g.dist_idx = nd_run;
+        g.pos = uend - carry_out;
+        g.pad = u;
+        out[nraw - skip] = g;
+      }
+    }
+    W.unit_ndist[u] = nd_run;
+  }
 }
 // One CTA per metablock: scan distance-symbol counts over units and add the prefix to each command.
 __global__ void __launch_bounds__(1024) k_fin_dist(Workspace W) {
@@ -1079,9 +1179,82 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split_greedy(Workspace W) {
 // the metablock prologue (block-split codes, context maps) and splices the per-tree descriptions behind it.
 // ---------------------------------------------------------------------------------------------------
 #define TREE_SLOT_BYTES 1536
+
+// Warp-cooperative huff_create_tree(): the (count asc, symbol desc) order is a total order, so any correct sort gives
+// the reference's node order -- here a bitonic sort of 64-bit keys in shared memory by all 32 lanes; the two-queue
+// merge and the depth assignment stay serial on lane 0.  Must be called by the whole warp.
+__device__ __forceinline__ void huff_create_tree_warp(const uint32_t* data, uint32_t length, int tree_limit, HuffNode* tree,
+                                                      uint8_t* depth, uint64_t* keys /* smem, 1024 */) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t FULL = 0xffffffffu;
+  for (uint32_t count_limit = 1;; count_limit *= 2) {
+    // compaction of the used symbols (order irrelevant)
+    uint32_t n = 0;
+    for (uint32_t base = 0; base < length; base += 32) {
+      const uint32_t i = base + lane;
+      const uint32_t c = i < length ? data[i] : 0u;
+      const uint32_t bal = __ballot_sync(FULL, c != 0);
+      if (c) keys[n + __popc(bal & ((1u << lane) - 1u))] = ((uint64_t)bmax(c, count_limit) << 16) | (0xFFFFu - i);
+      n += __popc(bal);
+    }
+    if (n == 1) {
+      if (lane == 0) depth[0xFFFFu - (uint32_t)(keys[0] & 0xFFFFu)] = 1;
+      __syncwarp();
+      return;
+    }
+    uint32_t np = 1;
+    while (np < n) np <<= 1;
+    for (uint32_t i = n + lane; i < np; i += 32) keys[i] = ~0ull;
+    __syncwarp();
+    for (uint32_t k = 2; k <= np; k <<= 1) {
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint32_t t = lane; t < (np >> 1); t += 32) {
+          const uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j clear
+          const uint32_t hi = lo | j;
+          const bool up = (lo & k) == 0;
+          const uint64_t a = keys[lo], b = keys[hi];
+          if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+        }
+        __syncwarp();
+      }
+    }
+    for (uint32_t i = lane; i < n; i += 32) {
+      const uint64_t kv = keys[i];
+      tree[i].count = (uint32_t)(kv >> 16);
+      tree[i].left = -1;
+      tree[i].right_or_value = (int16_t)(0xFFFFu - (uint32_t)(kv & 0xFFFFu));
+    }
+    __syncwarp();
+    int ok = 0;
+    if (lane == 0) {
+      HuffNode sentinel;
+      sentinel.count = 0xFFFFFFFFu; sentinel.left = -1; sentinel.right_or_value = -1;
+      tree[n] = sentinel;
+      tree[n + 1] = sentinel;
+      uint32_t i = 0, j = n + 1;
+      for (uint32_t k = n - 1; k != 0; --k) {
+        uint32_t left, right;
+        if (tree[i].count <= tree[j].count) left = i++; else left = j++;
+        if (tree[i].count <= tree[j].count) right = i++; else right = j++;
+        const uint32_t j_end = 2 * n - k;
+        tree[j_end].count = tree[left].count + tree[right].count;
+        tree[j_end].left = (int16_t)left;
+        tree[j_end].right_or_value = (int16_t)right;
+        tree[j_end + 1] = sentinel;
+      }
+      ok = huff_set_depth((int)(2 * n - 1), tree, depth, tree_limit) ? 1 : 0;
+    }
+    ok = __shfl_sync(FULL, ok, 0);
+    if (ok) return;
+  }
+}
+
 __global__ void __launch_bounds__(32) k_trees(Workspace W) {
+  __shared__ HuffStoreWs ws_s;  // tree / serialisation scratch in shared memory: the serial parts are latency bound
+  __shared__ uint64_t s_keys[1024];
+  __shared__ uint8_t s_depth[704];
   const uint32_t m = blockIdx.y;
-  if (threadIdx.x != 0) return;
+  const uint32_t lane = threadIdx.x;
   const MBDesc& mb = W.mb[m];
   const EncParams& P = W.P;
   const uint32_t nctx = ctxmap_num_contexts(mb.ctx_map_id);
@@ -1102,14 +1275,49 @@ __global__ void __launch_bounds__(32) k_trees(Workspace W) {
     depth = W.dist_depth + ((size_t)m * W.max_dist_types + t) * 64; code = W.dist_code + ((size_t)m * W.max_dist_types + t) * 64;
   }
   const uint32_t tree_cap = W.max_lit_trees + W.max_cmd_types + W.max_dist_types;
-  __shared__ HuffStoreWs ws_s;  // sort / tree scratch in shared memory: the serial tree code is latency bound
   HuffStoreWs* ws = &ws_s;
-  if (P.use_rle_opt) huff_optimize_counts_for_rle(A, hist, ws->rle);
+  if (P.use_rle_opt && lane == 0) huff_optimize_counts_for_rle(A, hist, ws->rle);
+  __syncwarp();
+  // == huff_build_and_store(), with the tree construction done by the whole warp ==
+  uint32_t count = 0, s4[4] = {0, 0, 0, 0}, max_bits = 0;
+  for (uint32_t i = 0; i < A; ++i) {  // (uniform across lanes; reads are broadcast)
+    if (hist[i]) {
+      if (count < 4) s4[count] = i;
+      else if (count > 4) break;
+      count++;
+    }
+  }
+  for (uint32_t c = A - 1; c; c >>= 1) ++max_bits;
+  for (uint32_t i = lane; i < A; i += 32) { s_depth[i] = 0; depth[i] = 0; code[i] = 0; }
+  __syncwarp();
   BitWriter bw;
   bw.init(W.tree_bits + ((size_t)m * tree_cap + slot) * TREE_SLOT_BYTES);
-  huff_build_and_store(bw, hist, A, A, ws, depth, code);
-  bw.flush_partial();
-  W.tree_nbits[(size_t)m * tree_cap + slot] = (uint32_t)bw.bit_pos();
+  if (count <= 1) {
+    if (lane == 0) { bw.put(4, 1); bw.put(max_bits, s4[0]); }
+  } else {
+    huff_create_tree_warp(hist, A, 15, ws->nodes, s_depth, s_keys);
+    __syncwarp();
+    if (lane == 0) {
+      huff_depths_to_codes(s_depth, A, code);
+      if (count <= 4) {
+        bw.put(2, 1);
+        bw.put(2, count - 1);
+        for (uint32_t i = 0; i < count; ++i)
+          for (uint32_t j = i + 1; j < count; ++j)
+            if (s_depth[s4[j]] < s_depth[s4[i]]) { uint32_t tt = s4[j]; s4[j] = s4[i]; s4[i] = tt; }
+        for (uint32_t i = 0; i < count; ++i) bw.put(max_bits, s4[i]);
+        if (count == 4) bw.put(1, s_depth[s4[0]] == 1 ? 1u : 0u);
+      } else {
+        huff_store_complex(bw, s_depth, A, ws);
+      }
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < A; i += 32) depth[i] = s_depth[i];
+  }
+  if (lane == 0) {
+    bw.flush_partial();
+    W.tree_nbits[(size_t)m * tree_cap + slot] = (uint32_t)bw.bit_pos();
+  }
 }
 
 __device__ __forceinline__ void append_bits(BitWriter& bw, const uint8_t* src, uint32_t nbits) {
@@ -1156,31 +1364,51 @@ __global__ void __launch_bounds__(32) k_header(Workspace W) {
 // ---------------------------------------------------------------------------------------------------
 // Emission.
 // ---------------------------------------------------------------------------------------------------
+// k_bitlen: exact bit length of every command + exclusive prefix inside its 256-command tile; tile totals go to
+// cmd_tile[]; k_bitscan turns the (few) tile totals of a metablock into tile offsets.
 __global__ void __launch_bounds__(256) k_bitlen(Workspace W) {
+  __shared__ uint32_t s_warp[8];
   const uint32_t m = blockIdx.y;
   const MBDesc& mb = W.mb[m];
+  if (blockIdx.x * 256u >= mb.ncmd) return;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= mb.ncmd) return;
-  const MetaCodes mc = make_codes(W, m);
-  const GCmd g = W.cmds[(size_t)m * W.cmd_cap + i];
-  CountWriter w;
-  w.bits = 0;
-  emit_command(w, mc, g.as_cmd(), i, g.lit_idx, g.dist_idx + W.unit_dist_off[g.pad], W.data, g.pos, W.P.abs_base);
-  W.cmd_bits[(size_t)m * W.cmd_cap + i] = (uint32_t)w.bits;
+  uint32_t bits = 0;
+  if (i < mb.ncmd) {
+    const MetaCodes mc = make_codes(W, m);
+    const GCmd g = W.cmds[(size_t)m * W.cmd_cap + i];
+    CountWriter w;
+    w.bits = 0;
+    emit_command(w, mc, g.as_cmd(), i, g.lit_idx, g.dist_idx + W.unit_dist_off[g.pad], W.data, g.pos, W.P.abs_base);
+    bits = (uint32_t)w.bits;
+  }
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t x = bits;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= (uint32_t)o) x += y;
+  }
+  if (lane == 31) s_warp[wid] = x;
+  __syncthreads();
+  uint32_t woff = 0;
+  for (uint32_t w = 0; w < wid; ++w) woff += s_warp[w];
+  if (i < mb.ncmd) W.cmd_bits[(size_t)m * W.cmd_cap + i] = woff + x - bits;
+  if (threadIdx.x == 255) W.cmd_tile[(size_t)m * W.tile_cap + blockIdx.x] = woff + x;
 }
-// One CTA per metablock: exclusive scan of command bit lengths (in place), total -> body_bits.
+// One CTA per metablock: exclusive scan of the tile totals (64-bit running sum), total -> body_bits.
 __global__ void __launch_bounds__(1024) k_bitscan(Workspace W) {
   __shared__ uint32_t s_warp[33];
   const uint32_t m = blockIdx.x;
   MBDesc& mb = W.mb[m];
-  uint32_t* bits = W.cmd_bits + (size_t)m * W.cmd_cap;
+  const uint32_t ntiles = (mb.ncmd + 255) / 256;
+  uint32_t* tiles = W.cmd_tile + (size_t)m * W.tile_cap;
   uint64_t run = 0;
-  for (uint32_t base = 0; base < mb.ncmd; base += 1024) {
+  for (uint32_t base = 0; base < ntiles; base += 1024) {
     uint32_t i = base + threadIdx.x;
-    uint32_t v = i < mb.ncmd ? bits[i] : 0;
+    uint32_t v = i < ntiles ? tiles[i] : 0;
     uint32_t tot;
     uint32_t ex = block_excl_scan_1024(v, s_warp, &tot);
-    if (i < mb.ncmd) bits[i] = (uint32_t)(run + ex);  // body of a metablock stays below 2^32 bits
+    if (i < ntiles) tiles[i] = (uint32_t)(run + ex);  // the body of a metablock stays below 2^32 bits
     run += tot;
   }
   if (threadIdx.x == 0) mb.body_bits = run;
@@ -1275,7 +1503,7 @@ __global__ void __launch_bounds__(256) k_emit_body(Workspace W) {
   const MetaCodes mc = make_codes(W, m);
   const GCmd g = W.cmds[(size_t)m * W.cmd_cap + i];
   AtomicOrWriter w;
-  w.init(W.out, mb.out_bitpos + mb.hdr_bits + W.cmd_bits[(size_t)m * W.cmd_cap + i]);
+  w.init(W.out, mb.out_bitpos + mb.hdr_bits + W.cmd_tile[(size_t)m * W.tile_cap + (i >> 8)] + W.cmd_bits[(size_t)m * W.cmd_cap + i]);
   emit_command(w, mc, g.as_cmd(), i, g.lit_idx, g.dist_idx + W.unit_dist_off[g.pad], W.data, g.pos, W.P.abs_base);
   w.flush();
 }
