@@ -1279,14 +1279,18 @@ __global__ void __launch_bounds__(32) k_trees(Workspace W) {
   if (P.use_rle_opt && lane == 0) huff_optimize_counts_for_rle(A, hist, ws->rle);
   __syncwarp();
   // == huff_build_and_store(), with the tree construction done by the whole warp ==
-  uint32_t count = 0, s4[4] = {0, 0, 0, 0}, max_bits = 0;
+  __shared__ uint32_t s4[4];  // first four used symbols (kept in shared memory: see profiles/ notes on the local-array clobber)
+  uint32_t count = 0, max_bits = 0;
+  if (lane < 4) s4[lane] = 0;
+  __syncwarp();
   for (uint32_t i = 0; i < A; ++i) {  // (uniform across lanes; reads are broadcast)
     if (hist[i]) {
-      if (count < 4) s4[count] = i;
+      if (count < 4) { if (lane == 0) s4[count] = i; }
       else if (count > 4) break;
       count++;
     }
   }
+  __syncwarp();
   for (uint32_t c = A - 1; c; c >>= 1) ++max_bits;
   for (uint32_t i = lane; i < A; i += 32) { s_depth[i] = 0; depth[i] = 0; code[i] = 0; }
   __syncwarp();
