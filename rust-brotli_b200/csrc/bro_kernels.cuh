@@ -225,53 +225,52 @@ __global__ void __launch_bounds__(256) k_scan_digits(const uint32_t* totals, uin
   digit_base[threadIdx.x] = s[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(SortArgs a) {
+__global__ void __launch_bounds__(SORT_THREADS, 6) k_sort_scatter(SortArgs a) {
   __shared__ uint32_t sw[SORT_TILE / 4 + 4];
   __shared__ uint32_t wc[SORT_THREADS / 32][256];
+  __shared__ uint32_t s_word[SORT_TILE];  // element words parked in shared memory (keeps the register count low => occupancy)
   const uint32_t tile = blockIdx.x;
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (uint32_t i = threadIdx.x; i < (SORT_THREADS / 32) * 256; i += SORT_THREADS) (&wc[0][0])[i] = 0;
   if (a.pass == 0) sort_stage_tile(a, tile, sw);
   __syncthreads();
   const uint32_t base = tile * SORT_TILE;
-  uint32_t word[SORT_ITEMS];
   uint16_t lrank[SORT_ITEMS];
   uint8_t dig[SORT_ITEMS];
   // element order inside the tile: warp-major, then round, then lane  (=> ascending position)
 #pragma unroll
   for (int r = 0; r < SORT_ITEMS; ++r) {
-    uint32_t e = wid * (32 * SORT_ITEMS) + r * 32 + lane;
-    bool valid = base + e < a.count;
+    const uint32_t e = wid * (32 * SORT_ITEMS) + r * 32 + lane;
+    const bool valid = base + e < a.count;
     uint32_t digit = 0x100u, w = 0;
     if (valid) {
       if (a.pass == 0) {
-        uint32_t key = smem_key(sw, e, a.hash_type, a.key_bits);
+        const uint32_t key = smem_key(sw, e, a.hash_type, a.key_bits);
         digit = key & 0xFFu;
         w = ((key >> 8) << 25) | (base + e);
       } else {
-        uint32_t v = a.in[base + e];
+        const uint32_t v = a.in[base + e];
         digit = v >> 25;
         w = v & 0x1FFFFFFu;
       }
     }
-    uint32_t peers = __match_any_sync(0xffffffffu, digit);
-    uint32_t rank_in_round = __popc(peers & ((1u << lane) - 1u));
+    s_word[e] = w;
+    const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+    const uint32_t rank_in_round = __popc(peers & ((1u << lane) - 1u));
     uint32_t old = 0;
     if (valid) old = wc[wid][digit];
     __syncwarp();
     if (valid && rank_in_round == 0) wc[wid][digit] = old + __popc(peers);
     __syncwarp();
-    word[r] = w;
     dig[r] = (uint8_t)digit;
-    lrank[r] = (uint16_t)(old + rank_in_round);
-    if (!valid) dig[r] = 0, lrank[r] = 0xFFFF;
+    lrank[r] = valid ? (uint16_t)(old + rank_in_round) : (uint16_t)0xFFFF;
   }
   __syncthreads();
   {  // per digit: exclusive scan over warps, seeded with the global offset of (digit, tile)
-    uint32_t d = threadIdx.x;
+    const uint32_t d = threadIdx.x;
     uint32_t acc = a.digit_base[d] + a.hist[(size_t)d * a.num_tiles + tile];
     for (int w = 0; w < SORT_THREADS / 32; ++w) {
-      uint32_t t = wc[w][d];
+      const uint32_t t = wc[w][d];
       wc[w][d] = acc;
       acc += t;
     }
@@ -279,7 +278,8 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(SortArgs a) {
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < SORT_ITEMS; ++r) {
-    if (lrank[r] != 0xFFFF) a.outw[wc[wid][dig[r]] + lrank[r]] = word[r];
+    const uint32_t e = wid * (32 * SORT_ITEMS) + r * 32 + lane;
+    if (lrank[r] != 0xFFFF) a.outw[wc[wid][dig[r]] + lrank[r]] = s_word[e];
   }
 }
 
@@ -349,63 +349,110 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
     s_pos[i] = pos; s_key[i] = key; s_d0[i] = w[0]; s_d1[i] = w[1]; s_d2[i] = w[2]; s_d3[i] = w[3];
   }
   __syncthreads();
+  // ---- candidate evaluation, load-balanced inside each warp ----
+  // Phase 1 (per lane): 16-bit mask of the next 16 older entries that share the bucket key and the first 4 bytes.
+  // Phase 2 (per warp): the (entry, candidate) pairs of all 32 lanes are compacted into a list and evaluated 32 at a
+  // time; results meet in a per-entry atomicMax on (score, nearness, len).  "Highest score, nearest on ties" is exactly
+  // what the sequential newest-first walk with strict improvement computes.
+  __shared__ uint16_t s_pairs[MATCH_THREADS / 32][512];
+  __shared__ uint32_t s_bestk[MATCH_THREADS / 32][32];
+  __shared__ uint32_t s_far[MATCH_THREADS / 32];
+  const uint32_t FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t i = threadIdx.x + (uint32_t)a.depth;
   const uint32_t prel = s_pos[i];
-  if (prel == 0xFFFFFFFFu || prel < a.payload_begin) return;
-  const uint32_t p = a.origin + prel;
-  const uint32_t maxl = bmin(a.lcap, a.n - p);
-  uint32_t best_score = BRO_MIN_SCORE, best_len = 0, best_dist = 0;
-  if (maxl >= 4) {
-    const uint32_t key = s_key[i];
-    const uint32_t max_backward = bmin(p, a.max_backward);
-    const uint32_t m0 = s_d0[i], m1 = s_d1[i], m2 = s_d2[i], m3 = s_d3[i];
-    bool done = false;
-    for (uint32_t cbase = 0; cbase < (uint32_t)a.depth && !done; cbase += 16) {
-      // phase 1 (branch-free, unrolled): which of the next 16 older entries share the bucket key and the first 4 bytes
-      uint32_t mask = 0;
+  const bool active = !(prel == 0xFFFFFFFFu || prel < a.payload_begin);
+  const uint32_t p = a.origin + (active ? prel : 0u);
+  const uint32_t maxl = active ? bmin(a.lcap, a.n - p) : 0u;
+  const uint32_t kNone = (BRO_MIN_SCORE << 16) | 0xFFFFu;
+  s_bestk[wid][lane] = kNone;
+  if (lane == 0) s_far[wid] = 0;
+  __syncwarp();
+  const uint32_t key = s_key[i], m0 = s_d0[i];
+  bool done = !active || maxl < 4;
+  const uint32_t wbase = wid * 32u + (uint32_t)a.depth;  // smem index of lane 0's entry
+  for (uint32_t cbase = 0; cbase < (uint32_t)a.depth; cbase += 16) {
+    if (!__any_sync(FULL, !done)) break;
+    uint32_t mask = 0;
+    if (!done) {
 #pragma unroll
       for (uint32_t c = 0; c < 16; ++c) {
         const uint32_t ci = i - 1u - cbase - c;
         mask |= (uint32_t)((s_key[ci] == key) & (s_d0[ci] == m0)) << c;
       }
-      if (s_key[i - 16u - cbase] != key) done = true;  // the bucket ends inside this group: nothing older can match
-      // phase 2: full evaluation of the survivors, nearest first
-      while (mask) {
-        const uint32_t c = (uint32_t)__ffs((int)mask) - 1u;
-        mask &= mask - 1u;
-        const uint32_t ci = i - 1u - cbase - c;
-        const uint32_t backward = prel - s_pos[ci];
-        if (backward > max_backward) { done = true; break; }
-        uint32_t len;
-        uint32_t x = s_d1[ci] ^ m1;
-        if (x) len = 4 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
-        else {
-          x = s_d2[ci] ^ m2;
-          if (x) len = 8 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
-          else {
-            x = s_d3[ci] ^ m3;
-            if (x) len = 12 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
-            else {
-              len = 16;
-              const uint8_t* pa = a.data + p;
-              const uint8_t* pb = pa - backward;
-              while (len + 8 <= maxl) {
-                const uint64_t y = ldu64(pa + len) ^ ldu64(pb + len);
-                if (y) { len += (uint32_t)(__ffsll((long long)y) - 1) >> 3; break; }
-                len += 8;
-              }
-              if (len + 8 > maxl) while (len < maxl && pa[len] == pb[len]) ++len;
-            }
-          }
-        }
-        if (len > maxl) len = maxl;
-        const uint32_t score = score_regular(a.hash_type, len, backward);
-        if (score > best_score) { best_score = score; best_len = len; best_dist = backward; }
-        if (len == maxl) { done = true; break; }
+      if (s_key[i - 16u - cbase] != key) done = true;  // bucket ends inside this group
+    }
+    // compact the pairs of the warp
+    const uint32_t cnt = __popc(mask);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(FULL, incl, o);
+      if (lane >= (uint32_t)o) incl += y;
+    }
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    {
+      uint32_t off = incl - cnt, mm = mask;
+      while (mm) {
+        const uint32_t c = (uint32_t)__ffs((int)mm) - 1u;
+        mm &= mm - 1u;
+        s_pairs[wid][off++] = (uint16_t)((lane << 4) | c);
       }
     }
+    __syncwarp();
+    for (uint32_t k = lane; k < total; k += 32) {
+      const uint32_t pr = s_pairs[wid][k];
+      const uint32_t ln = pr >> 4, c = pr & 15u;
+      const uint32_t ie = wbase + ln;
+      const uint32_t ci = ie - 1u - cbase - c;
+      const uint32_t eprel = s_pos[ie];
+      const uint32_t ep = a.origin + eprel;
+      const uint32_t emaxl = bmin(a.lcap, a.n - ep);
+      const uint32_t backward = eprel - s_pos[ci];
+      if (backward > bmin(ep, a.max_backward)) { atomicOr(&s_far[wid], 1u << ln); continue; }
+      uint32_t len;
+      uint32_t x = s_d1[ci] ^ s_d1[ie];
+      if (x) len = 4 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+      else {
+        x = s_d2[ci] ^ s_d2[ie];
+        if (x) len = 8 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+        else {
+          x = s_d3[ci] ^ s_d3[ie];
+          if (x) len = 12 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+          else {
+            len = 16;
+            const uint8_t* pa = a.data + ep;
+            const uint8_t* pb = pa - backward;
+            while (len + 8 <= emaxl) {
+              const uint64_t y = ldu64(pa + len) ^ ldu64(pb + len);
+              if (y) { len += (uint32_t)(__ffsll((long long)y) - 1) >> 3; break; }
+              len += 8;
+            }
+            if (len + 8 > emaxl) while (len < emaxl && pa[len] == pb[len]) ++len;
+          }
+        }
+      }
+      if (len > emaxl) len = emaxl;
+      const uint32_t score = score_regular(a.hash_type, len, backward);
+      atomicMax(&s_bestk[wid][ln], (score << 16) | ((255u - (cbase + c)) << 8) | len);
+    }
+    __syncwarp();
+    if (!done) {
+      const uint32_t bk = s_bestk[wid][lane];
+      if (bk != kNone && (bk & 0xFFu) == maxl) done = true;  // a full-length match: nothing farther can beat it
+      if ((s_far[wid] >> lane) & 1u) done = true;            // candidates beyond the window: all older ones too
+    }
+    __syncwarp();
   }
-  a.best[p] = best_len ? ((best_dist << 8) | best_len) : 0u;
+  if (active) {
+    const uint32_t bk = s_bestk[wid][lane];
+    uint32_t r = 0;
+    if (bk != kNone) {
+      const uint32_t cc = 255u - ((bk >> 8) & 0xFFu);
+      r = ((prel - s_pos[i - 1u - cc]) << 8) | (bk & 0xFFu);
+    }
+    a.best[p] = r;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -654,10 +701,10 @@ __device__ __forceinline__ uint32_t parse_unit_warp4(const EncParams& P, const u
       }
     }
     // lane 4*j now holds the finished result of position wbase + j
-    const uint32_t fb = __ballot_sync(FULL, f_found && i_lane == 0);
-    uint32_t found8 = 0;  // bit j <=> a match exists at wbase + j
-#pragma unroll
-    for (int j = 0; j < G; ++j) found8 |= ((fb >> (4 * j)) & 1u) << j;
+    uint32_t found8 = __ballot_sync(FULL, f_found && i_lane == 0);  // bits 0,4,8,.. -> compress to bits 0..7
+    found8 = (found8 | (found8 >> 3)) & 0x03030303u;
+    found8 = (found8 | (found8 >> 6)) & 0x000F000Fu;
+    found8 = (found8 | (found8 >> 12)) & 0xFFu;  // bit j <=> a match exists at wbase + j
 
     // ---------------- phase B: serial greedy / lazy walk over finished results (warp-uniform scalars) ----------------
     int j = 0;
