@@ -349,110 +349,63 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
     s_pos[i] = pos; s_key[i] = key; s_d0[i] = w[0]; s_d1[i] = w[1]; s_d2[i] = w[2]; s_d3[i] = w[3];
   }
   __syncthreads();
-  // ---- candidate evaluation, load-balanced inside each warp ----
-  // Phase 1 (per lane): 16-bit mask of the next 16 older entries that share the bucket key and the first 4 bytes.
-  // Phase 2 (per warp): the (entry, candidate) pairs of all 32 lanes are compacted into a list and evaluated 32 at a
-  // time; results meet in a per-entry atomicMax on (score, nearness, len).  "Highest score, nearest on ties" is exactly
-  // what the sequential newest-first walk with strict improvement computes.
-  __shared__ uint16_t s_pairs[MATCH_THREADS / 32][512];
-  __shared__ uint32_t s_bestk[MATCH_THREADS / 32][32];
-  __shared__ uint32_t s_far[MATCH_THREADS / 32];
-  const uint32_t FULL = 0xffffffffu;
-  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t i = threadIdx.x + (uint32_t)a.depth;
   const uint32_t prel = s_pos[i];
-  const bool active = !(prel == 0xFFFFFFFFu || prel < a.payload_begin);
-  const uint32_t p = a.origin + (active ? prel : 0u);
-  const uint32_t maxl = active ? bmin(a.lcap, a.n - p) : 0u;
-  const uint32_t kNone = (BRO_MIN_SCORE << 16) | 0xFFFFu;
-  s_bestk[wid][lane] = kNone;
-  if (lane == 0) s_far[wid] = 0;
-  __syncwarp();
-  const uint32_t key = s_key[i], m0 = s_d0[i];
-  bool done = !active || maxl < 4;
-  const uint32_t wbase = wid * 32u + (uint32_t)a.depth;  // smem index of lane 0's entry
-  for (uint32_t cbase = 0; cbase < (uint32_t)a.depth; cbase += 16) {
-    if (!__any_sync(FULL, !done)) break;
-    uint32_t mask = 0;
-    if (!done) {
+  if (prel == 0xFFFFFFFFu || prel < a.payload_begin) return;
+  const uint32_t p = a.origin + prel;
+  const uint32_t maxl = bmin(a.lcap, a.n - p);
+  uint32_t best_score = BRO_MIN_SCORE, best_len = 0, best_dist = 0;
+  if (maxl >= 4) {
+    const uint32_t key = s_key[i];
+    const uint32_t max_backward = bmin(p, a.max_backward);
+    const uint32_t m0 = s_d0[i], m1 = s_d1[i], m2 = s_d2[i], m3 = s_d3[i];
+    bool done = false;
+    for (uint32_t cbase = 0; cbase < (uint32_t)a.depth && !done; cbase += 16) {
+      // phase 1 (branch-free, unrolled): which of the next 16 older entries share the bucket key and the first 4 bytes
+      uint32_t mask = 0;
 #pragma unroll
       for (uint32_t c = 0; c < 16; ++c) {
         const uint32_t ci = i - 1u - cbase - c;
         mask |= (uint32_t)((s_key[ci] == key) & (s_d0[ci] == m0)) << c;
       }
-      if (s_key[i - 16u - cbase] != key) done = true;  // bucket ends inside this group
-    }
-    // compact the pairs of the warp
-    const uint32_t cnt = __popc(mask);
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t y = __shfl_up_sync(FULL, incl, o);
-      if (lane >= (uint32_t)o) incl += y;
-    }
-    const uint32_t total = __shfl_sync(FULL, incl, 31);
-    {
-      uint32_t off = incl - cnt, mm = mask;
-      while (mm) {
-        const uint32_t c = (uint32_t)__ffs((int)mm) - 1u;
-        mm &= mm - 1u;
-        s_pairs[wid][off++] = (uint16_t)((lane << 4) | c);
-      }
-    }
-    __syncwarp();
-    for (uint32_t k = lane; k < total; k += 32) {
-      const uint32_t pr = s_pairs[wid][k];
-      const uint32_t ln = pr >> 4, c = pr & 15u;
-      const uint32_t ie = wbase + ln;
-      const uint32_t ci = ie - 1u - cbase - c;
-      const uint32_t eprel = s_pos[ie];
-      const uint32_t ep = a.origin + eprel;
-      const uint32_t emaxl = bmin(a.lcap, a.n - ep);
-      const uint32_t backward = eprel - s_pos[ci];
-      if (backward > bmin(ep, a.max_backward)) { atomicOr(&s_far[wid], 1u << ln); continue; }
-      uint32_t len;
-      uint32_t x = s_d1[ci] ^ s_d1[ie];
-      if (x) len = 4 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
-      else {
-        x = s_d2[ci] ^ s_d2[ie];
-        if (x) len = 8 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+      if (s_key[i - 16u - cbase] != key) done = true;  // the bucket ends inside this group: nothing older can match
+      // phase 2: full evaluation of the survivors, nearest first
+      while (mask) {
+        const uint32_t c = (uint32_t)__ffs((int)mask) - 1u;
+        mask &= mask - 1u;
+        const uint32_t ci = i - 1u - cbase - c;
+        const uint32_t backward = prel - s_pos[ci];
+        if (backward > max_backward) { done = true; break; }
+        uint32_t len;
+        uint32_t x = s_d1[ci] ^ m1;
+        if (x) len = 4 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
         else {
-          x = s_d3[ci] ^ s_d3[ie];
-          if (x) len = 12 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+          x = s_d2[ci] ^ m2;
+          if (x) len = 8 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
           else {
-            len = 16;
-            const uint8_t* pa = a.data + ep;
-            const uint8_t* pb = pa - backward;
-            while (len + 8 <= emaxl) {
-              const uint64_t y = ldu64(pa + len) ^ ldu64(pb + len);
-              if (y) { len += (uint32_t)(__ffsll((long long)y) - 1) >> 3; break; }
-              len += 8;
+            x = s_d3[ci] ^ m3;
+            if (x) len = 12 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+            else {
+              len = 16;
+              const uint8_t* pa = a.data + p;
+              const uint8_t* pb = pa - backward;
+              while (len + 8 <= maxl) {
+                const uint64_t y = ldu64(pa + len) ^ ldu64(pb + len);
+                if (y) { len += (uint32_t)(__ffsll((long long)y) - 1) >> 3; break; }
+                len += 8;
+              }
+              if (len + 8 > maxl) while (len < maxl && pa[len] == pb[len]) ++len;
             }
-            if (len + 8 > emaxl) while (len < emaxl && pa[len] == pb[len]) ++len;
           }
         }
+        if (len > maxl) len = maxl;
+        const uint32_t score = score_regular(a.hash_type, len, backward);
+        if (score > best_score) { best_score = score; best_len = len; best_dist = backward; }
+        if (len == maxl) { done = true; break; }
       }
-      if (len > emaxl) len = emaxl;
-      const uint32_t score = score_regular(a.hash_type, len, backward);
-      atomicMax(&s_bestk[wid][ln], (score << 16) | ((255u - (cbase + c)) << 8) | len);
     }
-    __syncwarp();
-    if (!done) {
-      const uint32_t bk = s_bestk[wid][lane];
-      if (bk != kNone && (bk & 0xFFu) == maxl) done = true;  // a full-length match: nothing farther can beat it
-      if ((s_far[wid] >> lane) & 1u) done = true;            // candidates beyond the window: all older ones too
-    }
-    __syncwarp();
   }
-  if (active) {
-    const uint32_t bk = s_bestk[wid][lane];
-    uint32_t r = 0;
-    if (bk != kNone) {
-      const uint32_t cc = 255u - ((bk >> 8) & 0xFFu);
-      r = ((prel - s_pos[i - 1u - cc]) << 8) | (bk & 0xFFu);
-    }
-    a.best[p] = r;
-  }
+  a.best[p] = best_len ? ((best_dist << 8) | best_len) : 0u;
 }
 
 // ---------------------------------------------------------------------------------------------------
