@@ -376,6 +376,13 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
         const uint32_t ci = i - 1u - cbase - c;
         const uint32_t backward = prel - s_pos[ci];
         if (backward > max_backward) { done = true; break; }
+        if (best_len >= 4 && best_len < 16) {
+          // a farther candidate must be strictly longer to win: cheap reject on the byte at index best_len
+          // (the reference's `cur[best_len] != prev[best_len]` pre-filter, backward_references/mod.rs:1765-1773)
+          const uint32_t wsel = (2u + (best_len >> 2)) * E;
+          const uint32_t xb = smem[wsel + ci] ^ smem[wsel + i];
+          if ((xb >> ((best_len & 3u) * 8u)) & 0xFFu) continue;
+        }
         uint32_t len;
         uint32_t x = s_d1[ci] ^ m1;
         if (x) len = 4 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
