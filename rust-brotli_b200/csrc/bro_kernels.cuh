@@ -369,27 +369,13 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
         mask |= (uint32_t)((s_key[ci] == key) & (s_d0[ci] == m0)) << c;
       }
       if (s_key[i - 16u - cbase] != key) done = true;  // the bucket ends inside this group: nothing older can match
-      // phase 2: survivors, nearest first.  The cheap part (window check + "must be strictly longer" byte test, the
-      // reference's cur[best_len] != prev[best_len] pre-filter, mod.rs:1765-1773) runs in an inner skip loop so that the
-      // expensive length evaluation below is executed by converged lanes only.
-      for (;;) {
-        bool have = false;
-        uint32_t ci = 0, backward = 0;
-        while (mask) {
-          const uint32_t c = (uint32_t)__ffs((int)mask) - 1u;
-          mask &= mask - 1u;
-          ci = i - 1u - cbase - c;
-          backward = prel - s_pos[ci];
-          if (backward > max_backward) { mask = 0; done = true; break; }
-          if (best_len >= 4 && best_len < 16) {
-            const uint32_t wsel = (2u + (best_len >> 2)) * E;
-            const uint32_t xb = smem[wsel + ci] ^ smem[wsel + i];
-            if ((xb >> ((best_len & 3u) * 8u)) & 0xFFu) continue;
-          }
-          have = true;
-          break;
-        }
-        if (!have) break;
+      // phase 2: full evaluation of the survivors, nearest first
+      while (mask) {
+        const uint32_t c = (uint32_t)__ffs((int)mask) - 1u;
+        mask &= mask - 1u;
+        const uint32_t ci = i - 1u - cbase - c;
+        const uint32_t backward = prel - s_pos[ci];
+        if (backward > max_backward) { done = true; break; }
         uint32_t len;
         uint32_t x = s_d1[ci] ^ m1;
         if (x) len = 4 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
@@ -415,7 +401,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
         if (len > maxl) len = maxl;
         const uint32_t score = score_regular(a.hash_type, len, backward);
         if (score > best_score) { best_score = score; best_len = len; best_dist = backward; }
-        if (len == maxl) { done = true; mask = 0; }
+        if (len == maxl) { done = true; break; }
       }
     }
   }
