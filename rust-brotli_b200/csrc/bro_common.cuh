@@ -216,6 +216,7 @@ struct BitWriter {
       nacc -= 8;
     }
   }
+  BRO_HD void skip(uint32_t nbits) { while (nbits) { uint32_t k = nbits > 32 ? 32 : nbits; put(k, 0); nbits -= k; } }
   BRO_HD uint64_t bit_pos() const { return nbytes * 8 + nacc; }
   BRO_HD void flush_partial() {
     if (nacc) buf[nbytes] = (uint8_t)acc;  // keeps nacc so that bit_pos stays correct

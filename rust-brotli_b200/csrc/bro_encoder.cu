@@ -71,7 +71,7 @@ struct B200Encoder {
   // buffers
   DevBuf d_data, d_lut, d_sortA, d_sortB, d_hist, d_digit, d_best, d_raw, d_unit, d_cmds, d_cmd_bits, d_lit_syms,
       d_cmd_syms, d_dist_syms, d_mb, d_split_u8, d_split_u32, d_split_counts, d_hist_lit, d_hist_cmd, d_hist_dist,
-      d_split_codes, d_codes_u8, d_codes_u16, d_hdr, d_huff_ws, d_ctxmap_ws, d_out, d_total, d_tree_ws, d_tree_bits, d_tree_nbits, d_cmd_tile;
+      d_split_codes, d_codes_u8, d_codes_u16, d_hdr, d_huff_ws, d_ctxmap_ws, d_out, d_total, d_tree_ws, d_tree_bits, d_tree_nbits, d_cmd_tile, d_long_tab, d_seg_bits;
   uint8_t* h_pinned = nullptr;
   size_t h_pinned_cap = 0;
   uint64_t data_base = 0;  // absolute stream position of d_data[0]
@@ -101,7 +101,7 @@ struct B200Encoder {
     DevBuf* all[] = {&d_data, &d_lut, &d_sortA, &d_sortB, &d_hist, &d_digit, &d_best, &d_raw, &d_unit, &d_cmds, &d_cmd_bits,
                      &d_lit_syms, &d_cmd_syms, &d_dist_syms, &d_mb, &d_split_u8, &d_split_u32, &d_split_counts, &d_hist_lit,
                      &d_hist_cmd, &d_hist_dist, &d_split_codes, &d_codes_u8, &d_codes_u16, &d_hdr, &d_huff_ws, &d_ctxmap_ws,
-                     &d_out, &d_total, &d_tree_ws, &d_tree_bits, &d_tree_nbits, &d_cmd_tile};
+                     &d_out, &d_total, &d_tree_ws, &d_tree_bits, &d_tree_nbits, &d_cmd_tile, &d_long_tab, &d_seg_bits};
     for (auto* b : all) b->release();
     if (h_pinned) cudaFreeHost(h_pinned);
     for (auto& e : ev_pool) cudaEventDestroy(e);
@@ -162,6 +162,8 @@ struct B200Encoder {
     if (!d_cmd_bits.ensure((size_t)NM * cmd_cap * 4)) return false;
     W->tile_cap = cmd_cap / 256 + 2;
     if (!d_cmd_tile.ensure((size_t)NM * W->tile_cap * 4)) return false;
+    W->long_cap = mb_span / LONG_INS + 1;
+    if (!d_long_tab.ensure((size_t)NM * W->long_cap * 8) || !d_seg_bits.ensure((size_t)NM * W->long_cap * 4)) return false;
     if (!d_lit_syms.ensure(((size_t)c + 64) * 2)) return false;
     if (!d_cmd_syms.ensure((size_t)NM * cmd_cap * 2)) return false;
     if (!d_dist_syms.ensure((size_t)NM * cmd_cap * 2)) return false;
@@ -200,6 +202,8 @@ struct B200Encoder {
     W->cmds = d_cmds.as<GCmd>();
     W->cmd_bits = d_cmd_bits.as<uint32_t>();
     W->cmd_tile = d_cmd_tile.as<uint32_t>();
+    W->long_tab = d_long_tab.as<uint2>();
+    W->seg_bits = d_seg_bits.as<uint32_t>();
     W->lit_syms = d_lit_syms.as<uint16_t>();
     W->cmd_syms = d_cmd_syms.as<uint16_t>();
     W->dist_syms = d_dist_syms.as<uint16_t>();
@@ -339,7 +343,9 @@ struct B200Encoder {
     k_ctx_decide<<<W.num_mb, 256, 0, stream>>>(W);
     {
       dim3 g((W.cmd_cap + 255) / 256, W.num_mb);
+      cudaMemsetAsync(W.long_tab, 0, (size_t)W.num_mb * W.long_cap * sizeof(uint2), stream);
       k_symbols<<<g, 256, 0, stream>>>(W);
+      k_symbols_long<<<dim3(LONG_GRID, W.num_mb), 256, 0, stream>>>(W);
     }
     mark(B200_ST_SPLIT);
     {
@@ -356,16 +362,18 @@ struct B200Encoder {
     mark(B200_ST_EMIT);
     {
       dim3 g((W.cmd_cap + 255) / 256, W.num_mb);
+      k_bitlen_long<<<dim3(LONG_GRID, W.num_mb), 256, 0, stream>>>(W);
       k_bitlen<<<g, 256, 0, stream>>>(W);
       k_bitscan<<<W.num_mb, 1024, 0, stream>>>(W);
       k_layout<<<1, 32, 0, stream>>>(W, first ? 1 : 0, last ? 1 : 0, byte_align_end ? 1 : 0);
       k_emit_header<<<W.num_mb, 256, 0, stream>>>(W);
       k_emit_body<<<g, 256, 0, stream>>>(W);
+      k_emit_long<<<dim3(LONG_GRID, W.num_mb), 256, 0, stream>>>(W);
       dim3 gr(64, W.num_mb);
       k_emit_raw<<<gr, 256, 0, stream>>>(W);
     }
     mark(-1);
-    launches += 15;
+    launches += 18;
     CUDA_OK(cudaGetLastError());
     return true;
   }

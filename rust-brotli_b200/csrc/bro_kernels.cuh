@@ -67,6 +67,9 @@ struct Workspace {
   uint32_t* cmd_bits;   // [num_mb][cmd_cap] exclusive bit prefix inside the command's 256-tile
   uint32_t* cmd_tile;   // [num_mb][tile_cap] tile totals, then exclusive tile offsets
   uint32_t tile_cap;
+  uint2* long_tab;      // [num_mb][long_cap] long-insert commands by (pos - mb.start) / LONG_INS: x = command + 1, y = literal bits
+  uint32_t* seg_bits;   // [num_mb][long_cap] literal bits of each LONG_INS-literal segment of a long insert
+  uint32_t long_cap;
   // symbol streams
   uint16_t* lit_syms;   // [n]  literal | ctx << 8, metablock m at m.start
   uint16_t* cmd_syms;   // [num_mb][cmd_cap]
@@ -934,6 +937,94 @@ __global__ void __launch_bounds__(1024) k_fin_dist(Workspace W) {
   if (threadIdx.x == 0) mb.ndist = run;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Long inserts.  A command with more than LONG_INS literals would serialise its thread in k_symbols / k_bitlen /
+// k_emit_body (incompressible input is one 4 Mi-literal command per metablock), so those kernels skip its literals and
+// the *_long kernels below finish them, one CTA per LONG_INS-literal segment.  Long commands are found through a table
+// indexed by (pos - mb.start) / LONG_INS: two commands with more than LONG_INS literals never share a slot.
+// ---------------------------------------------------------------------------------------------------
+#define LONG_INS 512u
+#define LONG_GRID 64u
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_warp /*[9]*/, uint32_t* total) {
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= (uint32_t)o) x += y;
+  }
+  __syncthreads();
+  if (lane == 31) s_warp[wid] = x;
+  __syncthreads();
+  uint32_t woff = 0, tot = 0;
+#pragma unroll
+  for (uint32_t w = 0; w < 8; ++w) { const uint32_t t = s_warp[w]; if (w < wid) woff += t; tot += t; }
+  *total = tot;
+  return woff + x - v;
+}
+// Calls f(cmd_idx, g, slot, k) with the whole CTA (256 threads) for every segment k of every long command of metablock
+// blockIdx.y that this CTA owns; segments are dealt round-robin over the LONG_GRID CTAs of the metablock.
+template <typename F>
+__device__ __forceinline__ void for_each_long_segment(const Workspace& W, F f) {
+  __shared__ uint32_t s_mask[8];
+  const uint32_t m = blockIdx.y;
+  const MBDesc& mb = W.mb[m];
+  const uint32_t nslots = (mb.len + LONG_INS - 1) / LONG_INS;
+  const uint2* tab = W.long_tab + (size_t)m * W.long_cap;
+  for (uint32_t sb = 0; sb < nslots; sb += 256) {
+    const uint32_t s = sb + threadIdx.x;
+    const uint32_t v = s < nslots ? tab[s].x : 0u;
+    const uint32_t bal = __ballot_sync(0xffffffffu, v != 0);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_mask[threadIdx.x >> 5] = bal;
+    __syncthreads();
+    for (uint32_t w = 0; w < 8; ++w) {
+      uint32_t mask = s_mask[w];
+      while (mask) {
+        const uint32_t slot = sb + w * 32 + (uint32_t)__ffs((int)mask) - 1u;
+        mask &= mask - 1u;
+        const uint32_t ci = tab[slot].x - 1u;
+        const GCmd g = W.cmds[(size_t)m * W.cmd_cap + ci];
+        const uint32_t nseg = (g.insert_len + LONG_INS - 1) / LONG_INS;
+        for (uint32_t k = (blockIdx.x + LONG_GRID - slot % LONG_GRID) % LONG_GRID; k < nseg; k += LONG_GRID) f(ci, g, slot, k);
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_symbols_long(Workspace W) {
+  const uint32_t m = blockIdx.y;
+  const MBDesc& mb = W.mb[m];
+  const int id = mb.ctx_map_id;
+  const uint8_t* d = W.data;
+  for_each_long_segment(W, [&](uint32_t, const GCmd& g, uint32_t, uint32_t k) {
+    uint16_t* ls = W.lit_syms + mb.start + g.lit_idx;
+    for (uint32_t off = k * LONG_INS + threadIdx.x; off < min(g.insert_len, (k + 1) * LONG_INS); off += 256) {
+      const uint32_t pos = g.pos + off;
+      const uint8_t p1 = (W.P.abs_base || pos >= 1) ? d[(int64_t)pos - 1] : 0, p2 = (W.P.abs_base || pos >= 2) ? d[(int64_t)pos - 2] : 0;
+      const uint32_t cx = id ? ctxmap_lookup(id, context_utf8(p1, p2)) : 0u;
+      ls[off] = (uint16_t)(d[pos] | (cx << 8));
+    }
+  });
+}
+__global__ void __launch_bounds__(256) k_bitlen_long(Workspace W) {
+  __shared__ uint32_t s_warp[9];
+  const uint32_t m = blockIdx.y;
+  const MetaCodes mc = make_codes(W, m);
+  for_each_long_segment(W, [&](uint32_t, const GCmd& g, uint32_t slot, uint32_t k) {
+    CountWriter w;
+    w.bits = 0;
+    for (uint32_t off = k * LONG_INS + threadIdx.x; off < min(g.insert_len, (k + 1) * LONG_INS); off += 256)
+      emit_one_literal(w, mc, g.lit_idx + off, W.data, g.pos + off, W.P.abs_base);
+    uint32_t tot;
+    block_excl_scan_256((uint32_t)w.bits, s_warp, &tot);
+    if (threadIdx.x == 0) {
+      W.seg_bits[(size_t)m * W.long_cap + slot + k] = tot;
+      atomicAdd(&W.long_tab[(size_t)m * W.long_cap + slot].y, tot);
+    }
+  });
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Literal context decision: one CTA per metablock (encode.rs:1873-1927 in Q16).
 // ---------------------------------------------------------------------------------------------------
@@ -993,6 +1084,10 @@ __global__ void __launch_bounds__(256) k_symbols(Workspace W) {
   const uint8_t* d = W.data;
   uint16_t* ls = W.lit_syms + mb.start + c.lit_idx;
   const int id = mb.ctx_map_id;
+  if (c.insert_len > LONG_INS) {  // finished by k_symbols_long
+    W.long_tab[(size_t)m * W.long_cap + (c.pos - mb.start) / LONG_INS].x = i + 1;
+    return;
+  }
   uint8_t p1 = (W.P.abs_base || c.pos >= 1) ? d[(int64_t)c.pos - 1] : 0, p2 = (W.P.abs_base || c.pos >= 2) ? d[(int64_t)c.pos - 2] : 0;
   for (uint32_t j = 0; j < c.insert_len; ++j) {
     uint8_t lit = d[c.pos + j];
@@ -1382,7 +1477,8 @@ __global__ void __launch_bounds__(256) k_bitlen(Workspace W) {
     const GCmd g = W.cmds[(size_t)m * W.cmd_cap + i];
     CountWriter w;
     w.bits = 0;
-    emit_command(w, mc, g.as_cmd(), i, g.lit_idx, g.dist_idx + W.unit_dist_off[g.pad], W.data, g.pos, W.P.abs_base);
+    const uint32_t lb = g.insert_len > LONG_INS ? W.long_tab[(size_t)m * W.long_cap + (g.pos - mb.start) / LONG_INS].y : NOT_LONG;
+    emit_command(w, mc, g.as_cmd(), i, g.lit_idx, g.dist_idx + W.unit_dist_off[g.pad], W.data, g.pos, W.P.abs_base, lb);
     bits = (uint32_t)w.bits;
   }
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1434,6 +1530,10 @@ struct AtomicOrWriter {
     }
   }
   __device__ __forceinline__ void flush() { if (nacc) atomicOr(&out[word], (uint32_t)acc); }
+  __device__ __forceinline__ void skip(uint32_t n) {
+    flush();
+    init(out, word * 32 + nacc + n);
+  }
 };
 
 // Single thread: raw/compressed decision per metablock, stream layout, stream header / trailer / padding bits.
@@ -1508,8 +1608,42 @@ __global__ void __launch_bounds__(256) k_emit_body(Workspace W) {
   const GCmd g = W.cmds[(size_t)m * W.cmd_cap + i];
   AtomicOrWriter w;
   w.init(W.out, mb.out_bitpos + mb.hdr_bits + W.cmd_tile[(size_t)m * W.tile_cap + (i >> 8)] + W.cmd_bits[(size_t)m * W.cmd_cap + i]);
-  emit_command(w, mc, g.as_cmd(), i, g.lit_idx, g.dist_idx + W.unit_dist_off[g.pad], W.data, g.pos, W.P.abs_base);
+  const uint32_t lb = g.insert_len > LONG_INS ? W.long_tab[(size_t)m * W.long_cap + (g.pos - mb.start) / LONG_INS].y : NOT_LONG;
+  emit_command(w, mc, g.as_cmd(), i, g.lit_idx, g.dist_idx + W.unit_dist_off[g.pad], W.data, g.pos, W.P.abs_base, lb);
   w.flush();
+}
+// The literals of long inserts: CTA per segment, bit offsets from a block scan.
+__global__ void __launch_bounds__(256) k_emit_long(Workspace W) {
+  __shared__ uint32_t s_warp[9];
+  __shared__ uint64_t s_base;
+  const uint32_t m = blockIdx.y;
+  const MBDesc& mb = W.mb[m];
+  if (mb.raw) return;
+  const MetaCodes mc = make_codes(W, m);
+  for_each_long_segment(W, [&](uint32_t ci, const GCmd& g, uint32_t slot, uint32_t k) {
+    uint32_t before = 0;  // literal bits of the segments in front of this one
+    for (uint32_t j = threadIdx.x; j < k; j += 256) before += W.seg_bits[(size_t)m * W.long_cap + slot + j];
+    uint32_t tot;
+    block_excl_scan_256(before, s_warp, &tot);
+    if (threadIdx.x == 0) {
+      CountWriter h;
+      h.bits = 0;
+      emit_command_head(h, mc, g.as_cmd(), ci);
+      s_base = mb.out_bitpos + mb.hdr_bits + W.cmd_tile[(size_t)m * W.tile_cap + (ci >> 8)] + W.cmd_bits[(size_t)m * W.cmd_cap + ci] + h.bits + tot;
+    }
+    const uint32_t off = k * LONG_INS + 2 * threadIdx.x;
+    CountWriter c;
+    c.bits = 0;
+    for (uint32_t j = off; j < min(g.insert_len, off + 2); ++j) emit_one_literal(c, mc, g.lit_idx + j, W.data, g.pos + j, W.P.abs_base);
+    const uint32_t ex = block_excl_scan_256((uint32_t)c.bits, s_warp, &tot);  // (also orders s_base)
+    if (c.bits) {
+      AtomicOrWriter w;
+      w.init(W.out, s_base + ex);
+      for (uint32_t j = off; j < min(g.insert_len, off + 2); ++j) emit_one_literal(w, mc, g.lit_idx + j, W.data, g.pos + j, W.P.abs_base);
+      w.flush();
+    }
+    __syncthreads();
+  });
 }
 __global__ void __launch_bounds__(256) k_emit_raw(Workspace W) {
   const uint32_t m = blockIdx.y;

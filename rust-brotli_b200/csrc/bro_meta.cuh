@@ -212,30 +212,54 @@ BRO_HD uint32_t find_block(const uint32_t* starts, uint32_t num_blocks, uint32_t
   return lo;
 }
 
+// Bits of the literal of rank `rank` (block switch that falls on it + its code); used by the long-insert kernels.
+static constexpr uint32_t NOT_LONG = 0xFFFFFFFFu;
+template <typename W>
+BRO_HD void emit_one_literal(W& w, const MetaCodes& mc, uint32_t rank, const uint8_t* data, uint32_t pos, uint32_t abs_base) {
+  uint32_t b = 0;
+  if (mc.lit.num_blocks > 1) {
+    b = find_block(mc.lit.starts, mc.lit.num_blocks, rank);
+    if (b > 0 && mc.lit.starts[b] == rank) put_block_switch(w, mc.lit, *mc.lit_sc, b, false);
+  }
+  uint32_t tree = mc.lit.types[b] * mc.nctx;
+  if (mc.ctx_map_id) {
+    uint8_t p1 = (abs_base || pos >= 1) ? data[(int64_t)pos - 1] : 0, p2 = (abs_base || pos >= 2) ? data[(int64_t)pos - 2] : 0;
+    tree += ctxmap_lookup(mc.ctx_map_id, context_utf8(p1, p2));
+  }
+  const uint8_t lit = data[pos];
+  w.put(mc.lit_depth[tree * 256 + lit], mc.lit_code[tree * 256 + lit]);
+}
+// Bits a command writes before its literals (command block switch, command symbol, insert/copy extra bits).
+template <typename W>
+BRO_HD void emit_command_head(W& w, const MetaCodes& mc, const Cmd& c, uint32_t cmd_idx) {
+  uint32_t b = 0;
+  if (mc.cmd.num_blocks > 1) {
+    b = find_block(mc.cmd.starts, mc.cmd.num_blocks, cmd_idx);
+    if (b > 0 && mc.cmd.starts[b] == cmd_idx) put_block_switch(w, mc.cmd, *mc.cmd_sc, b, false);
+  }
+  uint32_t t = mc.cmd.types[b];
+  w.put(mc.cmd_depth[t * 704 + c.cmd_prefix], mc.cmd_code[t * 704 + c.cmd_prefix]);
+  // StoreCommandExtra: brotli_bit_stream.rs:1947-1961
+  uint32_t copylen_code = c.copy_len ? c.copy_len : 4u;
+  uint32_t inscode = insert_length_code(c.insert_len), copycode = copy_length_code(copylen_code);
+  uint32_t insnumextra = ins_extra(inscode);
+  uint64_t v = ((uint64_t)(copylen_code - copy_base(copycode)) << insnumextra) | (c.insert_len - ins_base(inscode));
+  uint32_t nb = insnumextra + copy_extra(copycode);
+  if (nb > 32) { w.put(32, (uint32_t)v); w.put(nb - 32, v >> 32); }
+  else w.put(nb, v);
+}
+
 // Emits (or counts) all bits of command `c`: block switches that fall on its symbols, the command symbol and
 // extra bits, its literals, its distance.  cmd_idx / lit_idx / dist_idx are symbol ranks inside the metablock,
 // pos = input position of the first literal of the command.
 template <typename W>
 BRO_HD_NOINLINE void emit_command(W& w, const MetaCodes& mc, const Cmd& c, uint32_t cmd_idx, uint32_t lit_idx,
-                                  uint32_t dist_idx, const uint8_t* data, uint32_t pos, uint32_t abs_base) {
-  {
-    uint32_t b = 0;
-    if (mc.cmd.num_blocks > 1) {
-      b = find_block(mc.cmd.starts, mc.cmd.num_blocks, cmd_idx);
-      if (b > 0 && mc.cmd.starts[b] == cmd_idx) put_block_switch(w, mc.cmd, *mc.cmd_sc, b, false);
-    }
-    uint32_t t = mc.cmd.types[b];
-    w.put(mc.cmd_depth[t * 704 + c.cmd_prefix], mc.cmd_code[t * 704 + c.cmd_prefix]);
-    // StoreCommandExtra: brotli_bit_stream.rs:1947-1961
-    uint32_t copylen_code = c.copy_len ? c.copy_len : 4u;
-    uint32_t inscode = insert_length_code(c.insert_len), copycode = copy_length_code(copylen_code);
-    uint32_t insnumextra = ins_extra(inscode);
-    uint64_t v = ((uint64_t)(copylen_code - copy_base(copycode)) << insnumextra) | (c.insert_len - ins_base(inscode));
-    uint32_t nb = insnumextra + copy_extra(copycode);
-    if (nb > 32) { w.put(32, (uint32_t)v); w.put(nb - 32, v >> 32); }
-    else w.put(nb, v);
-  }
-  if (c.insert_len) {
+                                  uint32_t dist_idx, const uint8_t* data, uint32_t pos, uint32_t abs_base,
+                                  uint32_t long_lit_bits = NOT_LONG) {
+  emit_command_head(w, mc, c, cmd_idx);
+  if (long_lit_bits != NOT_LONG) {
+    w.skip(long_lit_bits);  // the literals of a long insert are counted / written by the k_*_long kernels
+  } else if (c.insert_len) {
     uint32_t b = 0, bend = 0xFFFFFFFFu;
     if (mc.lit.num_blocks > 1) {
       b = find_block(mc.lit.starts, mc.lit.num_blocks, lit_idx);
@@ -275,6 +299,7 @@ BRO_HD_NOINLINE void emit_command(W& w, const MetaCodes& mc, const Cmd& c, uint3
 struct CountWriter {
   uint64_t bits;
   BRO_HD void put(uint32_t n, uint64_t) { bits += n; }
+  BRO_HD void skip(uint32_t n) { bits += n; }
 };
 
 }  // namespace bro

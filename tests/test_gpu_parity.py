@@ -76,6 +76,26 @@ def test_incompressible_and_degenerate(encoder, model):
         assert len(c) <= len(d) + 64
 
 
+def test_long_literal_runs(encoder, model):
+    """Inserts longer than LONG_INS literals take the segment kernels (k_symbols_long / k_bitlen_long / k_emit_long):
+    text interleaved with incompressible runs of many lengths, including runs that cross literal block switches."""
+    from tools import datagen
+    text = golden_bytes("alice29.txt")
+    rnd = datagen.pcg_random(3_000_000)
+    parts, o, t = [], 0, 0
+    for run in (511, 512, 513, 600, 1023, 1024, 1025, 5000, 70_000, 1_500_000, 200_000, 513):
+        parts.append(text[t:t + 20_000]); t = (t + 20_000) % 100_000
+        parts.append(rnd[o:o + run]); o += run
+    # low-entropy long runs compress instead of going raw: 3-symbol noise
+    parts.append(bytes(b % 3 + 65 for b in rnd[:900_000]))
+    parts.append(text)
+    d = b"".join(parts)
+    for q in (5, 9):
+        c = encoder.compress(d, q, 22)
+        assert sys_decompress(c, len(d)) == d
+        assert c == model.compress(d, q, 22)[0]
+
+
 def test_multi_metablock_text_size_parity(encoder, model):
     """20 MB of enwik-shaped text (5 metablocks, H6, 13 literal contexts): size within +0.5 % of libbrotlienc q5."""
     from tools import datagen

@@ -32,6 +32,7 @@ struct PlainOrWriter {  // same interface as the device atomic-OR writer
     for (uint32_t i = 0; i < n; ++i, ++pos)
       if ((v >> i) & 1) out[pos >> 3] |= (uint8_t)(1u << (pos & 7));
   }
+  void skip(uint32_t n) { pos += n; }
 };
 
 struct Model {

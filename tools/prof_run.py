@@ -10,7 +10,12 @@ def main():
     nbytes = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     q = int(sys.argv[3]) if len(sys.argv) > 3 else 5
-    d = datagen.enwik_like(nbytes)
+    kind = sys.argv[4] if len(sys.argv) > 4 else "text"
+    if kind == "text": d = datagen.enwik_like(nbytes)
+    elif kind == "random": d = datagen.pcg_random(nbytes)
+    elif kind == "json": d = datagen.json_logs(nbytes)
+    elif kind == "zeros": d = bytes(nbytes)
+    else: d = datagen.tiled(open(os.path.join(ROOT, "tests", "golden", kind), "rb").read(), nbytes)
     enc = rb.DeviceEncoder(0)
     enc.set_option(rb._native.OPT_TIMING, 1)
     t_in = torch.frombuffer(bytearray(d), dtype=torch.uint8).cuda()
