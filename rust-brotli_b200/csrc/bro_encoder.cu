@@ -56,28 +56,65 @@ struct DevBuf {
 };
 
 constexpr uint32_t kPad = 512;                 // zero bytes after the input
-constexpr uint32_t kChunk = 128u << 20;        // bytes per pipeline pass
+constexpr uint32_t kChunk = BRO_CHUNK_BYTES;   // bytes per pipeline pass (one sort batch for lgwin <= 22)
 constexpr uint32_t kBatchMax = 1u << 25;       // positions per sort batch (25-bit packed positions)
+constexpr uint32_t kLookahead = 4096;          // input bytes past a chunk's end that must be resident before it runs
+constexpr int kMaxLanes = 2;
+
+struct EventPool {
+  std::vector<cudaEvent_t> ev;
+  size_t used = 0;
+  cudaEvent_t get(bool timing) {
+    (void)timing;
+    if (used == ev.size()) {
+      cudaEvent_t e;
+      cudaEventCreateWithFlags(&e, timing ? cudaEventDefault : cudaEventDisableTiming);
+      ev.push_back(e);
+    }
+    return ev[used++];
+  }
+  void reset() { used = 0; }
+  void destroy() { for (auto& e : ev) cudaEventDestroy(e); ev.clear(); used = 0; }
+};
+
+// One lane = one stream + the per-chunk workspace.  Consecutive chunks alternate between lanes so that the
+// latency-bound stages of one chunk (block splitting, Huffman trees, layout) overlap the throughput-bound stages of
+// the next one (sort, match, parse) and the host<->device copies.
+struct Lane {
+  cudaStream_t stream = nullptr;
+  DevBuf d_sortA, d_sortB, d_hist, d_digit, d_best, d_raw, d_unit, d_cmds, d_cmd_bits, d_lit_syms, d_cmd_syms, d_dist_syms,
+      d_mb, d_split_u8, d_split_u32, d_split_counts, d_hist_lit, d_hist_cmd, d_hist_dist, d_split_codes, d_codes_u8,
+      d_codes_u16, d_hdr, d_huff_ws, d_ctxmap_ws, d_tree_ws, d_tree_bits, d_tree_nbits, d_cmd_tile, d_long_tab, d_seg_bits;
+  EventPool marks;  // timing marks: (event, stage that starts there); -1 ends the last stage
+  std::vector<int> mark_stage;
+  void release() {
+    DevBuf* all[] = {&d_sortA, &d_sortB, &d_hist, &d_digit, &d_best, &d_raw, &d_unit, &d_cmds, &d_cmd_bits, &d_lit_syms,
+                     &d_cmd_syms, &d_dist_syms, &d_mb, &d_split_u8, &d_split_u32, &d_split_counts, &d_hist_lit, &d_hist_cmd,
+                     &d_hist_dist, &d_split_codes, &d_codes_u8, &d_codes_u16, &d_hdr, &d_huff_ws, &d_ctxmap_ws, &d_tree_ws,
+                     &d_tree_bits, &d_tree_nbits, &d_cmd_tile, &d_long_tab, &d_seg_bits};
+    for (auto* b : all) b->release();
+    marks.destroy();
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
+  }
+};
 
 }  // namespace
 
 struct B200Encoder {
   int device = 0;
-  cudaStream_t stream = nullptr;
   bool ok = false;
   // configuration knobs (tests flip these)
   uint32_t unit = 4096, mb_units = 1024, lcap = 64;
   int use_rle_opt = 1, split = 1, ctx_model = 1;
-  // buffers
-  DevBuf d_data, d_lut, d_sortA, d_sortB, d_hist, d_digit, d_best, d_raw, d_unit, d_cmds, d_cmd_bits, d_lit_syms,
-      d_cmd_syms, d_dist_syms, d_mb, d_split_u8, d_split_u32, d_split_counts, d_hist_lit, d_hist_cmd, d_hist_dist,
-      d_split_codes, d_codes_u8, d_codes_u16, d_hdr, d_huff_ws, d_ctxmap_ws, d_out, d_total, d_tree_ws, d_tree_bits, d_tree_nbits, d_cmd_tile, d_long_tab, d_seg_bits;
-  uint8_t* h_pinned = nullptr;
-  size_t h_pinned_cap = 0;
+  int num_lanes = kMaxLanes;
+  Lane lanes[kMaxLanes];
+  cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams
+  DevBuf d_data, d_lut, d_out, d_total;          // d_total: [0] running bit position, [1 + k] position after chunk k
+  uint64_t* h_total = nullptr;                   // pinned mirror of d_total[1 + k]
+  size_t h_total_cap = 0;
+  EventPool sync_events;
   uint64_t data_base = 0;  // absolute stream position of d_data[0]
-  // timing of the last compress call: a mark = (event, stage that starts there); -1 ends the last stage
-  std::vector<cudaEvent_t> ev_pool;
-  std::vector<int> mark_stage;
   float stage_ms[B200_NUM_STAGES];
   uint32_t launches = 0;
   bool timing = false;
@@ -85,27 +122,39 @@ struct B200Encoder {
   bool init(int dev) {
     device = dev;
     CUDA_OK(cudaSetDevice(device));
-    CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (auto& L : lanes) CUDA_OK(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
     if (!d_lut.ensure(65536 * 4)) return false;
     std::vector<uint32_t> lut(65536);
     lut[0] = 0;
     for (uint32_t i = 1; i < 65536; ++i) lut[i] = (uint32_t)llround(std::log2((double)i) * 65536.0);
     CUDA_OK(cudaMemcpy(d_lut.p, lut.data(), 65536 * 4, cudaMemcpyHostToDevice));
-    if (!d_total.ensure(64)) return false;
     CUDA_OK(cudaDeviceSetLimit(cudaLimitStackSize, 4096));
+    for (int i = 0; i < B200_NUM_STAGES; ++i) stage_ms[i] = 0;
     ok = true;
     return true;
   }
   void destroy() {
     cudaSetDevice(device);
-    DevBuf* all[] = {&d_data, &d_lut, &d_sortA, &d_sortB, &d_hist, &d_digit, &d_best, &d_raw, &d_unit, &d_cmds, &d_cmd_bits,
-                     &d_lit_syms, &d_cmd_syms, &d_dist_syms, &d_mb, &d_split_u8, &d_split_u32, &d_split_counts, &d_hist_lit,
-                     &d_hist_cmd, &d_hist_dist, &d_split_codes, &d_codes_u8, &d_codes_u16, &d_hdr, &d_huff_ws, &d_ctxmap_ws,
-                     &d_out, &d_total, &d_tree_ws, &d_tree_bits, &d_tree_nbits, &d_cmd_tile, &d_long_tab, &d_seg_bits};
+    cudaDeviceSynchronize();
+    for (auto& L : lanes) L.release();
+    DevBuf* all[] = {&d_data, &d_lut, &d_out, &d_total};
     for (auto* b : all) b->release();
-    if (h_pinned) cudaFreeHost(h_pinned);
-    for (auto& e : ev_pool) cudaEventDestroy(e);
-    if (stream) cudaStreamDestroy(stream);
+    if (h_total) cudaFreeHost(h_total);
+    sync_events.destroy();
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_out) cudaStreamDestroy(s_out);
+  }
+  bool ensure_totals(size_t chunks) {
+    if (!d_total.ensure((chunks + 2) * 8)) return false;
+    if (chunks + 2 > h_total_cap) {
+      if (h_total) cudaFreeHost(h_total);
+      h_total = nullptr;
+      h_total_cap = chunks + 64;
+      CUDA_OK(cudaHostAlloc((void**)&h_total, h_total_cap * 8, cudaHostAllocDefault));
+    }
+    return true;
   }
 
   void fill_params(EncParams* P, int quality, int lgwin, uint64_t size_hint) const {
@@ -138,8 +187,8 @@ struct B200Encoder {
     P->ctx_model = ctx_model;
   }
 
-  // device buffers for one chunk of `c` bytes
-  bool ensure_chunk(uint32_t c, const EncParams& P, Workspace* W) {
+  // device buffers of lane L for one chunk of `c` bytes
+  bool ensure_chunk(Lane& L, uint32_t c, const EncParams& P, Workspace* W) {
     const uint32_t mb_span = P.unit * P.mb_units;
     const uint32_t NU = (c + P.unit - 1) / P.unit;
     const uint32_t NM = (NU + P.mb_units - 1) / P.mb_units;
@@ -155,138 +204,129 @@ struct B200Encoder {
     W->max_cmd_types = P.split ? 256 : 1;
     W->max_dist_types = P.split ? 256 : 1;
     W->hdr_cap = P.split ? (384u << 10) : (16u << 10);
-    if (!d_best.ensure(((size_t)c + 64) * 4)) return false;
-    if (!d_raw.ensure((size_t)NU * cu * sizeof(RawCmd))) return false;
-    if (!d_unit.ensure((size_t)NU * 7 * 4)) return false;
-    if (!d_cmds.ensure((size_t)NM * cmd_cap * sizeof(GCmd))) return false;
-    if (!d_cmd_bits.ensure((size_t)NM * cmd_cap * 4)) return false;
+    if (!L.d_best.ensure(((size_t)c + 64) * 4)) return false;
+    if (!L.d_raw.ensure((size_t)NU * cu * sizeof(RawCmd))) return false;
+    if (!L.d_unit.ensure((size_t)NU * 7 * 4)) return false;
+    if (!L.d_cmds.ensure((size_t)NM * cmd_cap * sizeof(GCmd))) return false;
+    if (!L.d_cmd_bits.ensure((size_t)NM * cmd_cap * 4)) return false;
     W->tile_cap = cmd_cap / 256 + 2;
-    if (!d_cmd_tile.ensure((size_t)NM * W->tile_cap * 4)) return false;
+    if (!L.d_cmd_tile.ensure((size_t)NM * W->tile_cap * 4)) return false;
     W->long_cap = mb_span / LONG_INS + 1;
-    if (!d_long_tab.ensure((size_t)NM * W->long_cap * 8) || !d_seg_bits.ensure((size_t)NM * W->long_cap * 4)) return false;
-    if (!d_lit_syms.ensure(((size_t)c + 64) * 2)) return false;
-    if (!d_cmd_syms.ensure((size_t)NM * cmd_cap * 2)) return false;
-    if (!d_dist_syms.ensure((size_t)NM * cmd_cap * 2)) return false;
-    if (!d_mb.ensure((size_t)NM * sizeof(MBDesc))) return false;
+    if (!L.d_long_tab.ensure((size_t)NM * W->long_cap * 8) || !L.d_seg_bits.ensure((size_t)NM * W->long_cap * 4)) return false;
+    if (!L.d_lit_syms.ensure(((size_t)c + 64) * 2)) return false;
+    if (!L.d_cmd_syms.ensure((size_t)NM * cmd_cap * 2)) return false;
+    if (!L.d_dist_syms.ensure((size_t)NM * cmd_cap * 2)) return false;
+    if (!L.d_mb.ensure((size_t)NM * sizeof(MBDesc))) return false;
     const size_t blk_total = (size_t)W->lit_blk_cap + W->cmd_blk_cap + W->dist_blk_cap;
-    if (!d_split_u8.ensure((size_t)NM * blk_total)) return false;
-    if (!d_split_u32.ensure((size_t)NM * blk_total * 2 * 4)) return false;
-    if (!d_split_counts.ensure((size_t)NM * 6 * 4)) return false;
-    if (!d_hist_lit.ensure((size_t)NM * (W->max_lit_trees + 13) * 256 * 4)) return false;
-    if (!d_hist_cmd.ensure((size_t)NM * (W->max_cmd_types + 1) * 704 * 4)) return false;
-    if (!d_hist_dist.ensure((size_t)NM * (W->max_dist_types + 1) * 64 * 4)) return false;
-    if (!d_split_codes.ensure((size_t)NM * 3 * sizeof(SplitCode))) return false;
+    if (!L.d_split_u8.ensure((size_t)NM * blk_total)) return false;
+    if (!L.d_split_u32.ensure((size_t)NM * blk_total * 2 * 4)) return false;
+    if (!L.d_split_counts.ensure((size_t)NM * 6 * 4)) return false;
+    if (!L.d_hist_lit.ensure((size_t)NM * (W->max_lit_trees + 13) * 256 * 4)) return false;
+    if (!L.d_hist_cmd.ensure((size_t)NM * (W->max_cmd_types + 1) * 704 * 4)) return false;
+    if (!L.d_hist_dist.ensure((size_t)NM * (W->max_dist_types + 1) * 64 * 4)) return false;
+    if (!L.d_split_codes.ensure((size_t)NM * 3 * sizeof(SplitCode))) return false;
     const size_t code_syms = (size_t)W->max_lit_trees * 256 + (size_t)W->max_cmd_types * 704 + (size_t)W->max_dist_types * 64;
-    if (!d_codes_u8.ensure((size_t)NM * code_syms)) return false;
-    if (!d_codes_u16.ensure((size_t)NM * code_syms * 2)) return false;
-    if (!d_hdr.ensure((size_t)NM * W->hdr_cap)) return false;
-    if (!d_huff_ws.ensure((size_t)NM * sizeof(HuffStoreWs))) return false;
-    if (!d_ctxmap_ws.ensure((size_t)NM * 256 * 64 * 4)) return false;
+    if (!L.d_codes_u8.ensure((size_t)NM * code_syms)) return false;
+    if (!L.d_codes_u16.ensure((size_t)NM * code_syms * 2)) return false;
+    if (!L.d_hdr.ensure((size_t)NM * W->hdr_cap)) return false;
+    if (!L.d_huff_ws.ensure((size_t)NM * sizeof(HuffStoreWs))) return false;
+    if (!L.d_ctxmap_ws.ensure((size_t)NM * 256 * 64 * 4)) return false;
     const size_t tree_cap = (size_t)W->max_lit_trees + W->max_cmd_types + W->max_dist_types;
-    if (!d_tree_bits.ensure((size_t)NM * tree_cap * TREE_SLOT_BYTES)) return false;
-    if (!d_tree_nbits.ensure((size_t)NM * tree_cap * 4)) return false;
+    if (!L.d_tree_bits.ensure((size_t)NM * tree_cap * TREE_SLOT_BYTES)) return false;
+    if (!L.d_tree_nbits.ensure((size_t)NM * tree_cap * 4)) return false;
     // sort scratch
-    const uint32_t nb = std::min<uint64_t>((uint64_t)c + (1ull << P.lgwin), kBatchMax);
+    const uint32_t nb = std::min<uint64_t>((uint64_t)c + (1ull << P.lgwin) + 4096, kBatchMax);
     const uint32_t tiles = (nb + SORT_TILE - 1) / SORT_TILE;
-    if (!d_sortA.ensure((size_t)nb * 4 + 64)) return false;
-    if (!d_sortB.ensure((size_t)nb * 4 + 64)) return false;
-    if (!d_hist.ensure((size_t)256 * tiles * 4)) return false;
-    if (!d_digit.ensure(512 * 4)) return false;
+    if (!L.d_sortA.ensure((size_t)nb * 4 + 64)) return false;
+    if (!L.d_sortB.ensure((size_t)nb * 4 + 64)) return false;
+    if (!L.d_hist.ensure((size_t)256 * tiles * 4)) return false;
+    if (!L.d_digit.ensure(512 * 4)) return false;
     // wire pointers
     W->lut = d_lut.as<uint32_t>();
-    W->best = d_best.as<uint32_t>();
-    W->raw = d_raw.as<RawCmd>();
-    uint32_t* up = d_unit.as<uint32_t>();
+    W->best = L.d_best.as<uint32_t>();
+    W->raw = L.d_raw.as<RawCmd>();
+    uint32_t* up = L.d_unit.as<uint32_t>();
     W->unit_ncmd = up; W->unit_tail = up + NU; W->unit_ncopy = up + 2 * (size_t)NU;
     W->unit_cmd_off = up + 3 * (size_t)NU; W->unit_lit_off = up + 4 * (size_t)NU; W->unit_ndist = up + 5 * (size_t)NU; W->unit_dist_off = up + 6 * (size_t)NU;
-    W->cmds = d_cmds.as<GCmd>();
-    W->cmd_bits = d_cmd_bits.as<uint32_t>();
-    W->cmd_tile = d_cmd_tile.as<uint32_t>();
-    W->long_tab = d_long_tab.as<uint2>();
-    W->seg_bits = d_seg_bits.as<uint32_t>();
-    W->lit_syms = d_lit_syms.as<uint16_t>();
-    W->cmd_syms = d_cmd_syms.as<uint16_t>();
-    W->dist_syms = d_dist_syms.as<uint16_t>();
-    W->mb = d_mb.as<MBDesc>();
-    uint8_t* t8 = d_split_u8.as<uint8_t>();
+    W->cmds = L.d_cmds.as<GCmd>();
+    W->cmd_bits = L.d_cmd_bits.as<uint32_t>();
+    W->cmd_tile = L.d_cmd_tile.as<uint32_t>();
+    W->long_tab = L.d_long_tab.as<uint2>();
+    W->seg_bits = L.d_seg_bits.as<uint32_t>();
+    W->lit_syms = L.d_lit_syms.as<uint16_t>();
+    W->cmd_syms = L.d_cmd_syms.as<uint16_t>();
+    W->dist_syms = L.d_dist_syms.as<uint16_t>();
+    W->mb = L.d_mb.as<MBDesc>();
+    uint8_t* t8 = L.d_split_u8.as<uint8_t>();
     W->lit_types = t8; W->cmd_types = t8 + (size_t)NM * W->lit_blk_cap; W->dist_types = W->cmd_types + (size_t)NM * W->cmd_blk_cap;
-    uint32_t* t32 = d_split_u32.as<uint32_t>();
+    uint32_t* t32 = L.d_split_u32.as<uint32_t>();
     W->lit_lengths = t32; t32 += (size_t)NM * W->lit_blk_cap;
     W->lit_starts = t32; t32 += (size_t)NM * W->lit_blk_cap;
     W->cmd_lengths = t32; t32 += (size_t)NM * W->cmd_blk_cap;
     W->cmd_starts = t32; t32 += (size_t)NM * W->cmd_blk_cap;
     W->dist_lengths = t32; t32 += (size_t)NM * W->dist_blk_cap;
     W->dist_starts = t32;
-    W->split_counts = d_split_counts.as<uint32_t>();
-    W->lit_hist = d_hist_lit.as<uint32_t>(); W->cmd_hist = d_hist_cmd.as<uint32_t>(); W->dist_hist = d_hist_dist.as<uint32_t>();
-    W->split_codes = d_split_codes.as<SplitCode>();
-    uint8_t* c8 = d_codes_u8.as<uint8_t>();
+    W->split_counts = L.d_split_counts.as<uint32_t>();
+    W->lit_hist = L.d_hist_lit.as<uint32_t>(); W->cmd_hist = L.d_hist_cmd.as<uint32_t>(); W->dist_hist = L.d_hist_dist.as<uint32_t>();
+    W->split_codes = L.d_split_codes.as<SplitCode>();
+    uint8_t* c8 = L.d_codes_u8.as<uint8_t>();
     W->lit_depth = c8; W->cmd_depth = c8 + (size_t)NM * W->max_lit_trees * 256;
     W->dist_depth = W->cmd_depth + (size_t)NM * W->max_cmd_types * 704;
-    uint16_t* c16 = d_codes_u16.as<uint16_t>();
+    uint16_t* c16 = L.d_codes_u16.as<uint16_t>();
     W->lit_code = c16; W->cmd_code = c16 + (size_t)NM * W->max_lit_trees * 256;
     W->dist_code = W->cmd_code + (size_t)NM * W->max_cmd_types * 704;
-    W->hdr = d_hdr.as<uint8_t>();
-    W->huff_ws = d_huff_ws.as<HuffStoreWs>();
-    W->ctxmap_ws = d_ctxmap_ws.as<uint32_t>();
-    W->tree_ws = d_tree_ws.as<HuffStoreWs>();
-    W->tree_bits = d_tree_bits.as<uint8_t>();
-    W->tree_nbits = d_tree_nbits.as<uint32_t>();
+    W->hdr = L.d_hdr.as<uint8_t>();
+    W->huff_ws = L.d_huff_ws.as<HuffStoreWs>();
+    W->ctxmap_ws = L.d_ctxmap_ws.as<uint32_t>();
+    W->tree_ws = L.d_tree_ws.as<HuffStoreWs>();
+    W->tree_bits = L.d_tree_bits.as<uint8_t>();
+    W->tree_nbits = L.d_tree_nbits.as<uint32_t>();
     W->total_bits = d_total.as<uint64_t>();
     return true;
   }
 
-  void mark(int stage) {
+  void mark(Lane& L, int stage) {
     if (!timing) return;
-    size_t i = mark_stage.size();
-    if (i >= ev_pool.size()) {
-      cudaEvent_t e;
-      cudaEventCreate(&e);
-      ev_pool.push_back(e);
-    }
-    cudaEventRecord(ev_pool[i], stream);
-    mark_stage.push_back(stage);
+    cudaEventRecord(L.marks.get(true), L.stream);
+    L.mark_stage.push_back(stage);
   }
+  void reset_timings() {
+    for (auto& L : lanes) { L.marks.reset(); L.mark_stage.clear(); }
+  }
+  // per-stage sums of event-bracketed time on each lane's own stream (with two lanes stages of different chunks overlap,
+  // so the sum over stages can exceed the wall time)
   void collect_timings() {
     for (int i = 0; i < B200_NUM_STAGES; ++i) stage_ms[i] = 0;
-    for (size_t i = 0; i + 1 < mark_stage.size(); ++i) {
-      if (mark_stage[i] < 0) continue;
-      float ms = 0;
-      cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]);
-      stage_ms[mark_stage[i]] += ms;
+    for (auto& L : lanes) {
+      for (size_t i = 0; i + 1 < L.mark_stage.size(); ++i) {
+        if (L.mark_stage[i] < 0) continue;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, L.marks.ev[i], L.marks.ev[i + 1]);
+        stage_ms[L.mark_stage[i]] += ms;
+      }
     }
-    mark_stage.clear();
+    reset_timings();
   }
 
-  // Compresses data[range_start, range_start + range_len) of the stream resident at d_data (absolute positions) and
-  // appends its metablocks to W.out at *W.total_bits.  first/last control the stream header / trailer.
-  bool run_chunk(const EncParams& Pstream, uint32_t range_start, uint32_t range_len, uint32_t* d_outw,
-                 uint64_t out_cap_bytes, bool first, bool last, bool byte_align_end) {
+  // Enqueues, on lane L, the compression of data[range_start, range_start + range_len) of the stream resident at d_data
+  // (absolute positions); its metablocks are appended to the output at the running bit position.  `after_layout` (may
+  // be null) is the previous chunk's layout event; `layout_done` is recorded when this chunk's layout is final.
+  bool run_chunk(Lane& L, const EncParams& Pstream, uint32_t range_start, uint32_t range_len, uint32_t* d_outw,
+                 uint64_t out_cap_bytes, bool first, bool last, bool byte_align_end, uint32_t chunk_idx,
+                 cudaEvent_t after_layout, cudaEvent_t layout_done) {
+    cudaStream_t stream = L.stream;
     Workspace W;
     memset(&W, 0, sizeof(W));
     EncParams P = Pstream;
     P.n = range_len;
     P.abs_base = range_start;
-    if (!ensure_chunk(range_len, P, &W)) return false;
+    if (!ensure_chunk(L, range_len, P, &W)) return false;
     W.P = P;
     W.data = d_data.as<uint8_t>() + (range_start - data_base);
     W.out = d_outw;
     W.out_cap_bytes = out_cap_bytes;
     const uint8_t* d_all = d_data.as<uint8_t>() - data_base;  // indexable by absolute position >= data_base
-    // metablock descriptors
-    {
-      std::vector<MBDesc> mbs(W.num_mb);
-      for (uint32_t m = 0; m < W.num_mb; ++m) {
-        MBDesc& d = mbs[m];
-        memset(&d, 0, sizeof(d));
-        d.u0 = m * P.mb_units;
-        d.u1 = std::min(W.num_units, d.u0 + P.mb_units);
-        d.start = d.u0 * P.unit;
-        d.len = std::min<uint64_t>(range_len, (uint64_t)d.u1 * P.unit) - d.start;
-      }
-      CUDA_OK(cudaMemcpyAsync(W.mb, mbs.data(), mbs.size() * sizeof(MBDesc), cudaMemcpyHostToDevice, stream));
-      CUDA_OK(cudaStreamSynchronize(stream));  // mbs is a stack-lifetime vector
-    }
+    k_init_mb<<<(W.num_mb + 63) / 64, 64, 0, stream>>>(W);
     // ---- sort + match, batch by batch ----
     const uint32_t window = 1u << P.lgwin;
     const uint32_t payload_max = kBatchMax - window - 4096;
@@ -297,28 +337,28 @@ struct B200Encoder {
       if (origin < data_base) origin = (uint32_t)data_base;
       const uint32_t count = b1 - origin;
       const uint32_t tiles = (count + SORT_TILE - 1) / SORT_TILE;
-      mark(B200_ST_SORT);
+      mark(L, B200_ST_SORT);
       SortArgs sa;
       sa.data = d_all + origin;
       sa.count = count;
-      sa.hist = d_hist.as<uint32_t>();
-      sa.digit_base = d_digit.as<uint32_t>();
+      sa.hist = L.d_hist.as<uint32_t>();
+      sa.digit_base = L.d_digit.as<uint32_t>();
       sa.num_tiles = tiles;
       sa.hash_type = P.hash_type;
       sa.key_bits = P.key_bits;
       for (int pass = 0; pass < 2; ++pass) {
         sa.pass = pass;
-        sa.in = pass == 0 ? nullptr : d_sortA.as<uint32_t>();
-        sa.outw = pass == 0 ? d_sortA.as<uint32_t>() : d_sortB.as<uint32_t>();
+        sa.in = pass == 0 ? nullptr : L.d_sortA.as<uint32_t>();
+        sa.outw = pass == 0 ? L.d_sortA.as<uint32_t>() : L.d_sortB.as<uint32_t>();
         k_sort_hist<<<tiles, SORT_THREADS, 0, stream>>>(sa);
-        k_scan_rows<<<256, 256, 0, stream>>>(sa.hist, tiles, d_digit.as<uint32_t>() + 256);
-        k_scan_digits<<<1, 256, 0, stream>>>(d_digit.as<uint32_t>() + 256, d_digit.as<uint32_t>());
+        k_scan_rows<<<256, 256, 0, stream>>>(sa.hist, tiles, L.d_digit.as<uint32_t>() + 256);
+        k_scan_digits<<<1, 256, 0, stream>>>(L.d_digit.as<uint32_t>() + 256, L.d_digit.as<uint32_t>());
         k_sort_scatter<<<tiles, SORT_THREADS, 0, stream>>>(sa);
         launches += 4;
       }
       MatchArgs ma;
       ma.data = d_all;
-      ma.sorted = d_sortB.as<uint32_t>();
+      ma.sorted = L.d_sortB.as<uint32_t>();
       ma.count = count;
       ma.origin = origin;
       ma.payload_begin = (uint32_t)b0 - origin;
@@ -330,13 +370,13 @@ struct B200Encoder {
       ma.lcap = P.lcap;
       ma.max_backward = P.max_backward;
       const size_t smem = (size_t)(MATCH_THREADS + P.depth) * 6 * 4;
-      mark(B200_ST_MATCH);
+      mark(L, B200_ST_MATCH);
       k_match<<<(count + MATCH_THREADS - 1) / MATCH_THREADS, MATCH_THREADS, smem, stream>>>(ma);
       launches += 1;
     }
-    mark(B200_ST_PARSE);
+    mark(L, B200_ST_PARSE);
     k_parse<<<(W.num_units + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, stream>>>(W);
-    mark(B200_ST_FINALIZE);
+    mark(L, B200_ST_FINALIZE);
     k_fin_count<<<W.num_mb, 1024, 0, stream>>>(W);
     k_fin_write<<<(W.num_units + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, stream>>>(W);
     k_fin_dist<<<W.num_mb, 1024, 0, stream>>>(W);
@@ -347,55 +387,39 @@ struct B200Encoder {
       k_symbols<<<g, 256, 0, stream>>>(W);
       k_symbols_long<<<dim3(LONG_GRID, W.num_mb), 256, 0, stream>>>(W);
     }
-    mark(B200_ST_SPLIT);
+    mark(L, B200_ST_SPLIT);
     {
       dim3 g(W.num_mb, 3);
       if (P.split) k_split_greedy<<<g, SPLIT_THREADS, 0, stream>>>(W);
       else k_split_simple<<<g, 512, 0, stream>>>(W);
     }
-    mark(B200_ST_HEADER);
+    mark(L, B200_ST_HEADER);
     {
       dim3 g(W.max_lit_trees + W.max_cmd_types + W.max_dist_types, W.num_mb);
       k_trees<<<g, 32, 0, stream>>>(W);
     }
     k_header<<<W.num_mb, 32, 0, stream>>>(W);
-    mark(B200_ST_EMIT);
+    mark(L, B200_ST_EMIT);
     {
       dim3 g((W.cmd_cap + 255) / 256, W.num_mb);
       k_bitlen_long<<<dim3(LONG_GRID, W.num_mb), 256, 0, stream>>>(W);
       k_bitlen<<<g, 256, 0, stream>>>(W);
       k_bitscan<<<W.num_mb, 1024, 0, stream>>>(W);
-      k_layout<<<1, 32, 0, stream>>>(W, first ? 1 : 0, last ? 1 : 0, byte_align_end ? 1 : 0);
+      if (after_layout) CUDA_OK(cudaStreamWaitEvent(stream, after_layout, 0));  // bit positions chain through the chunks
+      k_layout<<<1, 32, 0, stream>>>(W, first ? 1 : 0, last ? 1 : 0, byte_align_end ? 1 : 0, d_total.as<uint64_t>() + 1 + chunk_idx);
+      CUDA_OK(cudaEventRecord(layout_done, stream));
       k_emit_header<<<W.num_mb, 256, 0, stream>>>(W);
       k_emit_body<<<g, 256, 0, stream>>>(W);
       k_emit_long<<<dim3(LONG_GRID, W.num_mb), 256, 0, stream>>>(W);
       dim3 gr(64, W.num_mb);
       k_emit_raw<<<gr, 256, 0, stream>>>(W);
     }
-    mark(-1);
-    launches += 18;
+    mark(L, -1);
+    launches += 19;
     CUDA_OK(cudaGetLastError());
     return true;
   }
-
-  // Whole-stream compression of n bytes already resident at d_data[0..n) (padded).  Output to d_outw.
-  bool compress_resident(int quality, int lgwin, uint64_t size_hint, size_t n, uint32_t* d_outw, uint64_t out_cap_bytes,
-                         bool first, bool last, bool byte_align_end, uint32_t range_start, uint32_t range_len) {
-    EncParams P;
-    fill_params(&P, quality, lgwin, size_hint ? size_hint : n);
-    (void)n;
-    for (uint64_t s = range_start; s < (uint64_t)range_start + range_len; s += kChunk) {
-      uint32_t len = (uint32_t)std::min<uint64_t>(kChunk, (uint64_t)range_start + range_len - s);
-      bool f = first && s == range_start;
-      bool l = s + len == (uint64_t)range_start + range_len;
-      if (!run_chunk(P, (uint32_t)s, len, d_outw, out_cap_bytes, f, last && l, byte_align_end && l)) return false;
-    }
-    return true;
-  }
 };
-
-// k_layout takes flags; declared here because it needs the final signature
-namespace bro {}
 
 // ---------------------------------------------------------------------------------------------------
 // C ABI
@@ -431,26 +455,88 @@ int b200_encoder_set_option(B200Encoder* e, int option, uint32_t value) {
     case B200_OPT_SPLIT: e->split = (int)value; return 1;
     case B200_OPT_CTX_MODEL: e->ctx_model = (int)value; return 1;
     case B200_OPT_TIMING: e->timing = value != 0; return 1;
+    case B200_OPT_LANES: e->num_lanes = value < 1 ? 1 : (value > (uint32_t)kMaxLanes ? kMaxLanes : (int)value); return 1;
   }
   return 0;
 }
 
 size_t b200_max_compressed_size(size_t n) { return n + (n >> 10) * 8 + 4096; }
 
-// Stage the input on the device: from device memory (kind = 1) or host memory (kind = 0).
-// Only the bytes a range can see are staged: [base, end) with base = 4 KiB-aligned start of its window halo.
-static bool stage_input(B200Encoder* e, const uint8_t* in, size_t base, size_t end, int kind) {
-  const size_t n = end - base;
-  if (!e->d_data.ensure(n + kPad)) return false;
-  e->data_base = base;
-  CUDA_OK(cudaMemcpyAsync(e->d_data.p, in + base, n, kind == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
-  CUDA_OK(cudaMemsetAsync(e->d_data.as<uint8_t>() + n, 0, kPad, e->stream));
-  return true;
-}
-
 // Compresses [range_start, range_start+range_len) of an n-byte stream.  in/out are device pointers when
 // device_io != 0, host pointers otherwise.  first/last: emit stream header / final empty metablock;
 // byte_align: end the range with a padding metablock so that ranges can be concatenated with memcpy.
+//
+// Pipeline: the input is staged chunk by chunk on a copy stream, chunks alternate between two compute lanes, and the
+// finished part of the output is copied back while later chunks are still running.
+static bool compress_range_impl(B200Encoder* e, int quality, int lgwin, uint64_t size_hint, const uint8_t* in, size_t n,
+                                size_t range_start, size_t range_len, bool first, bool last, bool byte_align, uint8_t* out,
+                                size_t out_cap, size_t* out_size, int device_io, bool keep_on_device) {
+  e->launches = 0;
+  e->reset_timings();
+  e->sync_events.reset();
+  EncParams P;
+  e->fill_params(&P, quality, lgwin, size_hint ? size_hint : n);
+  const size_t window = (size_t)1 << P.lgwin;
+  const size_t base = range_start > window ? ((range_start - window) & ~(size_t)4095) : 0;
+  const size_t end = range_start + range_len;
+  const size_t staged = end - base;
+  const size_t need = b200_max_compressed_size(range_len) + 64;
+  const size_t nchunks = (range_len + kChunk - 1) / kChunk;
+  const cudaMemcpyKind in_kind = device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const cudaMemcpyKind out_kind = device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if (!e->d_data.ensure(staged + kPad) || !e->d_out.ensure(need) || !e->ensure_totals(nchunks)) return false;
+  e->data_base = base;
+  uint8_t* dd = e->d_data.as<uint8_t>();
+  CUDA_OK(cudaMemsetAsync(e->d_out.p, 0, need, e->s_in));
+  CUDA_OK(cudaMemsetAsync(e->d_total.p, 0, 8, e->s_in));
+  CUDA_OK(cudaMemsetAsync(dd + staged, 0, kPad, e->s_in));
+  std::vector<cudaEvent_t> ev_done(nchunks);
+  cudaEvent_t prev_layout = nullptr;
+  size_t copied = base;  // absolute position up to which the input is staged
+  for (size_t k = 0; k < nchunks; ++k) {
+    const size_t s = range_start + k * (size_t)kChunk;
+    const size_t len = std::min<size_t>(kChunk, end - s);
+    // stage the input this chunk can see: its window halo (first chunk), its own bytes, a short look-ahead
+    const size_t upto = std::min(end, s + len + kLookahead);
+    if (upto > copied) {
+      CUDA_OK(cudaMemcpyAsync(dd + (copied - base), in + copied, upto - copied, in_kind, e->s_in));
+      copied = upto;
+    }
+    cudaEvent_t ev_in = e->sync_events.get(false);
+    CUDA_OK(cudaEventRecord(ev_in, e->s_in));
+    Lane& L = e->lanes[k % (size_t)e->num_lanes];
+    CUDA_OK(cudaStreamWaitEvent(L.stream, ev_in, 0));
+    cudaEvent_t ev_layout = e->sync_events.get(false);
+    const bool f = first && k == 0, l = k + 1 == nchunks;
+    if (!e->run_chunk(L, P, (uint32_t)s, (uint32_t)len, e->d_out.as<uint32_t>(), need, f, last && l, byte_align && l, (uint32_t)k,
+                      prev_layout, ev_layout))
+      return false;
+    prev_layout = ev_layout;
+    CUDA_OK(cudaMemcpyAsync(e->h_total + k, e->d_total.as<uint64_t>() + 1 + k, 8, cudaMemcpyDeviceToHost, L.stream));
+    ev_done[k] = e->sync_events.get(false);
+    CUDA_OK(cudaEventRecord(ev_done[k], L.stream));
+  }
+  // drain: as each chunk finishes, every output byte below its end bit position is final
+  size_t done_bytes = 0;
+  for (size_t k = 0; k < nchunks; ++k) {
+    if (cudaEventSynchronize(ev_done[k]) != cudaSuccess) {
+      fprintf(stderr, "[brotli_b200] kernel failure: %s\n", cudaGetErrorString(cudaGetLastError()));
+      return false;
+    }
+    const uint64_t tb = e->h_total[k];
+    const size_t upto = k + 1 == nchunks ? (size_t)((tb + 7) >> 3) : (size_t)(tb >> 3);
+    if (upto > out_cap) return false;
+    if (!keep_on_device && upto > done_bytes)
+      CUDA_OK(cudaMemcpyAsync(out + done_bytes, e->d_out.as<uint8_t>() + done_bytes, upto - done_bytes, out_kind, e->s_out));
+    done_bytes = upto;
+  }
+  CUDA_OK(cudaStreamSynchronize(e->s_out));
+  CUDA_OK(cudaStreamSynchronize(e->s_in));
+  *out_size = done_bytes;
+  if (e->timing) e->collect_timings();
+  return true;
+}
+
 int b200_encoder_compress_range(B200Encoder* e, int quality, int lgwin, uint64_t size_hint, const uint8_t* in, size_t n,
                                 size_t range_start, size_t range_len, int first, int last, int byte_align, uint8_t* out,
                                 size_t out_cap, size_t* out_size, int device_io) {
@@ -469,32 +555,11 @@ int b200_encoder_compress_range(B200Encoder* e, int quality, int lgwin, uint64_t
     *out_size = 0;
     return 1;
   }
-  e->launches = 0;
-  e->mark_stage.clear();
-  const size_t need = b200_max_compressed_size(range_len) + 64;
-  {
-    int lw = lgwin < 10 ? 10 : (lgwin > 24 ? 24 : lgwin);
-    size_t window = (size_t)1 << lw;
-    size_t base = range_start > window ? ((range_start - window) & ~(size_t)4095) : 0;
-    if (!stage_input(e, in, base, range_start + range_len, device_io)) return 0;
-  }
-  if (!e->d_out.ensure(need)) return 0;
-  if (cudaMemsetAsync(e->d_out.p, 0, need, e->stream) != cudaSuccess) return 0;
-  if (cudaMemsetAsync(e->d_total.p, 0, 8, e->stream) != cudaSuccess) return 0;
-  if (!e->compress_resident(quality, lgwin, size_hint, n, e->d_out.as<uint32_t>(), need, first != 0, last != 0,
-                            byte_align != 0, (uint32_t)range_start, (uint32_t)range_len))
-    return 0;
-  uint64_t total_bits = 0;
-  if (cudaMemcpyAsync(&total_bits, e->d_total.p, 8, cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) return 0;
-  if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
-    fprintf(stderr, "[brotli_b200] kernel failure: %s\n", cudaGetErrorString(cudaGetLastError()));
+  if (!compress_range_impl(e, quality, lgwin, size_hint, in, n, range_start, range_len, first != 0, last != 0, byte_align != 0,
+                           out, out_cap, out_size, device_io, false)) {
+    cudaDeviceSynchronize();  // leave no work in flight behind a failed call
     return 0;
   }
-  size_t bytes = (size_t)((total_bits + 7) >> 3);
-  if (bytes > out_cap) return 0;
-  if (cudaMemcpy(out, e->d_out.p, bytes, device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
-  *out_size = bytes;
-  if (e->timing) e->collect_timings();
   return 1;
 }
 
@@ -510,18 +575,16 @@ int b200_encoder_last_timings(B200Encoder* e, float* ms, uint32_t* launches) {
   return 1;
 }
 
-// test hook: device results of the match stage for an n-byte buffer (host in, host out)
+// test hook: device results of the match stage for an n-byte buffer (host in, host out); n <= one chunk
 int b200_stage_match(B200Encoder* e, int quality, int lgwin, const uint8_t* in, size_t n, uint32_t* best_out) {
   if (!e || !e->ok || n == 0 || n > kChunk) return 0;
   if (cudaSetDevice(e->device) != cudaSuccess) return 0;
-  if (!stage_input(e, in, 0, n, 0)) return 0;
-  const size_t need = b200_max_compressed_size(n) + 64;
-  if (!e->d_out.ensure(need)) return 0;
-  cudaMemsetAsync(e->d_out.p, 0, need, e->stream);
-  cudaMemsetAsync(e->d_total.p, 0, 8, e->stream);
-  if (!e->compress_resident(quality, lgwin, n, n, e->d_out.as<uint32_t>(), need, true, true, false, 0, (uint32_t)n)) return 0;
-  if (cudaStreamSynchronize(e->stream) != cudaSuccess) return 0;
-  return cudaMemcpy(best_out, e->d_best.p, n * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+  size_t got = 0;
+  if (!compress_range_impl(e, quality, lgwin, n, in, n, 0, n, true, true, false, nullptr, b200_max_compressed_size(n) + 64, &got, 0, true)) {
+    cudaDeviceSynchronize();
+    return 0;
+  }
+  return cudaMemcpy(best_out, e->lanes[0].d_best.p, n * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
 }
 
 }  // extern "C"

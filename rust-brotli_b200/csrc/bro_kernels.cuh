@@ -35,6 +35,8 @@ struct MBDesc {
   int ctx_map_id;
   uint32_t hdr_bits;
   uint32_t raw;               // stored uncompressed
+  uint32_t has_long;          // some command has more than LONG_INS literals
+  uint32_t pad_;
   uint64_t body_bits;
   uint64_t out_bitpos;        // position of the metablock in the output stream
 };
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
   const uint32_t p = a.origin + prel;
   const uint32_t maxl = bmin(a.lcap, a.n - p);
   uint32_t best_score = BRO_MIN_SCORE, best_len = 0, best_dist = 0;
-  if (maxl >= 4) {
+  if (a.n - p >= 8) {  // keys of the last 7 positions would depend on bytes past the range: they get no bucket match
     const uint32_t key = s_key[i];
     const uint32_t max_backward = bmin(p, a.max_backward);
     const uint32_t m0 = s_d0[i], m1 = s_d1[i], m2 = s_d2[i], m3 = s_d3[i];
@@ -788,6 +790,18 @@ __device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* s
   return r;
 }
 
+// Metablock descriptors of a chunk: fixed spans of mb_units parse units.
+__global__ void k_init_mb(Workspace W) {
+  const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= W.num_mb) return;
+  MBDesc d;
+  memset(&d, 0, sizeof(d));
+  d.u0 = m * W.P.mb_units;
+  d.u1 = min(W.num_units, d.u0 + W.P.mb_units);
+  d.start = d.u0 * W.P.unit;
+  d.len = (uint32_t)min((uint64_t)W.P.n, (uint64_t)d.u1 * W.P.unit) - d.start;
+  W.mb[m] = d;
+}
 // One CTA (1024 threads) per metablock: per-unit final command counts and literal counts -> exclusive scans.
 __global__ void __launch_bounds__(1024) k_fin_count(Workspace W) {
   __shared__ uint32_t s_warp[33];
@@ -810,7 +824,7 @@ __global__ void __launch_bounds__(1024) k_fin_count(Workspace W) {
     cmd_run += tc;
     lit_run += tl;
   }
-  if (threadIdx.x == 0) { mb.ncmd = cmd_run; mb.nlit = lit_run; }
+  if (threadIdx.x == 0) { mb.ncmd = cmd_run; mb.nlit = lit_run; mb.has_long = 0; }
 }
 // Incoming distance cache of raw command i of unit u: the last (up to) four distinct-run distances before it, looking
 // back inside the unit and, if needed, into earlier units of the metablock (same rule as finalize_unit()).
@@ -970,6 +984,7 @@ __device__ __forceinline__ void for_each_long_segment(const Workspace& W, F f) {
   __shared__ uint32_t s_mask[8];
   const uint32_t m = blockIdx.y;
   const MBDesc& mb = W.mb[m];
+  if (!mb.has_long) return;
   const uint32_t nslots = (mb.len + LONG_INS - 1) / LONG_INS;
   const uint2* tab = W.long_tab + (size_t)m * W.long_cap;
   for (uint32_t sb = 0; sb < nslots; sb += 256) {
@@ -1086,6 +1101,7 @@ __global__ void __launch_bounds__(256) k_symbols(Workspace W) {
   const int id = mb.ctx_map_id;
   if (c.insert_len > LONG_INS) {  // finished by k_symbols_long
     W.long_tab[(size_t)m * W.long_cap + (c.pos - mb.start) / LONG_INS].x = i + 1;
+    W.mb[m].has_long = 1;
     return;
   }
   uint8_t p1 = (W.P.abs_base || c.pos >= 1) ? d[(int64_t)c.pos - 1] : 0, p2 = (W.P.abs_base || c.pos >= 2) ? d[(int64_t)c.pos - 2] : 0;
@@ -1537,7 +1553,7 @@ struct AtomicOrWriter {
 };
 
 // Single thread: raw/compressed decision per metablock, stream layout, stream header / trailer / padding bits.
-__global__ void k_layout(Workspace W, int first, int last, int byte_align) {
+__global__ void k_layout(Workspace W, int first, int last, int byte_align, uint64_t* total_after) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const EncParams& P = W.P;
   uint64_t pos = *W.total_bits;
@@ -1573,6 +1589,7 @@ __global__ void k_layout(Workspace W, int first, int last, int byte_align) {
     pos = (pos + 6 + 7) & ~7ull;
   }
   *W.total_bits = pos;
+  *total_after = pos;  // per-chunk copy: the host reads it while later chunks keep advancing total_bits
 }
 
 __global__ void __launch_bounds__(256) k_emit_header(Workspace W) {

@@ -8,6 +8,9 @@
 #pragma once
 #include "bro_common.cuh"
 
+// bytes per pipeline pass: one chunk = 6 metablocks of 4 MiB; with its 4 MiB window halo it is one 2^25 sort batch
+#define BRO_CHUNK_BYTES (24u << 20)
+
 namespace bro {
 
 struct EncParams {

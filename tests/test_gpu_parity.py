@@ -76,6 +76,20 @@ def test_incompressible_and_degenerate(encoder, model):
         assert len(c) <= len(d) + 64
 
 
+def test_multi_chunk_stream_equals_model(encoder, model):
+    """Streams longer than one 24 MiB chunk: chunks run on alternating lanes (streams) and append to one bit stream; the
+    result must not depend on the number of lanes and must equal the model's chunk loop."""
+    import rust_brotli_b200 as rb
+    from tools import datagen
+    d = datagen.enwik_like(30_000_000) + datagen.pcg_random(22_000_000)[:21_000_000] + golden_bytes("alice29.txt") * 20
+    ref = model.compress(d, 5, 22)[0]
+    for lanes in (2, 1, 2):
+        encoder.set_option(rb._native.OPT_LANES, lanes)
+        c = encoder.compress(d, 5, 22)
+        assert c == ref, "lanes=%d" % lanes
+    assert sys_decompress(ref, len(d)) == d
+
+
 def test_long_literal_runs(encoder, model):
     """Inserts longer than LONG_INS literals take the segment kernels (k_symbols_long / k_bitlen_long / k_emit_long):
     text interleaved with incompressible runs of many lengths, including runs that cross literal block switches."""

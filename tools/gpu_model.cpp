@@ -61,7 +61,7 @@ void stage_match(Model& M) {
     uint32_t c = cnt[key];
     uint32_t best_score = BRO_MIN_SCORE, best_len = 0, best_dist = 0;
     uint32_t max_backward = bmin(p, P.max_backward);
-    if (maxl >= 4) {
+    if (N - p >= 8) {  // keys of the last 7 positions would depend on bytes past the range: no bucket match
       uint32_t lim = bmin(c, D);
       for (uint32_t k = 1; k <= lim; ++k) {
         uint32_t cand = ring[(size_t)key * D + ((c - k) & (D - 1))];
@@ -307,18 +307,39 @@ size_t gpu_model_compress(const EncParams* Pin, const uint8_t* input, uint8_t* o
   return gpu_model_compress_range(Pin, input, 0, Pin->n, 1, 1, 0, out, out_cap, st, best_out);
 }
 
-// Mirrors b200_encoder_compress_range: Pin->n is the size of the whole stream `input`.
+static uint64_t model_chunk(const EncParams* Pin, const uint8_t* input, uint32_t range_start, uint32_t range_len,
+                            int first, int last, int byte_align, uint8_t* out, size_t out_cap, ModelStats* st,
+                            uint32_t* best_out, uint64_t bitpos_in);
+
+// Mirrors b200_encoder_compress_range: Pin->n is the size of the whole stream `input`.  Like the device encoder the
+// range is compressed as independent chunks of BRO_CHUNK_BYTES that append to one bit stream.
 size_t gpu_model_compress_range(const EncParams* Pin, const uint8_t* input, uint32_t range_start, uint32_t range_len,
                                 int first, int last, int byte_align, uint8_t* out, size_t out_cap, ModelStats* st,
                                 uint32_t* best_out) {
-  Model M;
-  M.P = *Pin;
   const uint32_t stream_n = Pin->n;
   if (st) memset(st, 0, sizeof(*st));
   if (stream_n == 0 || range_len == 0) {
     if (first && last && stream_n == 0) { out[0] = 6; return 1; }
     return 0;
   }
+  memset(out, 0, out_cap);
+  uint64_t bits = 0;
+  const uint64_t end = (uint64_t)range_start + range_len;
+  for (uint64_t s = range_start; s < end; s += BRO_CHUNK_BYTES) {
+    const uint32_t len = (uint32_t)std::min<uint64_t>(BRO_CHUNK_BYTES, end - s);
+    const bool l = s + len == end;
+    bits = model_chunk(Pin, input, (uint32_t)s, len, first && s == range_start, last && l, byte_align && l, out, out_cap, st,
+                       best_out ? best_out + (s - range_start) : nullptr, bits);
+    if (bits == ~0ull) return 0;
+  }
+  return (size_t)((bits + 7) >> 3);
+}
+
+static uint64_t model_chunk(const EncParams* Pin, const uint8_t* input, uint32_t range_start, uint32_t range_len,
+                            int first, int last, int byte_align, uint8_t* out, size_t out_cap, ModelStats* st,
+                            uint32_t* best_out, uint64_t bitpos_in) {
+  Model M;
+  M.P = *Pin;
   // match stage over the whole prefix (absolute positions), then shift everything to range-relative
   M.P.n = range_start + range_len;
   M.P.abs_base = 0;
@@ -352,8 +373,7 @@ size_t gpu_model_compress_range(const EncParams* Pin, const uint8_t* input, uint
     stage_bitlen(M, mb);
   }
   // layout: stream header, metablocks, final empty metablock
-  memset(out, 0, out_cap);
-  PlainOrWriter w{out, 0};
+  PlainOrWriter w{out, bitpos_in};
   if (first) {
     if (P.lgwin == 16) w.put(1, 0);
     else if (P.lgwin == 17) w.put(7, 1);
@@ -366,7 +386,7 @@ size_t gpu_model_compress_range(const EncParams* Pin, const uint8_t* input, uint
     uint64_t raw_hdr = raw_metablock_header_bits(mb.len);
     uint64_t raw_bits = ((w.pos + raw_hdr + 7) & ~7ull) - w.pos + 8ull * mb.len;
     mb.raw = comp_bits > raw_bits;
-    if ((w.pos + bmax(comp_bits, raw_bits)) / 8 + 16 > out_cap) return 0;
+    if ((w.pos + bmax(comp_bits, raw_bits)) / 8 + 16 > out_cap) return ~0ull;
     if (st) {
       st->num_metablocks++;
       st->num_raw_metablocks += mb.raw;
@@ -410,7 +430,7 @@ size_t gpu_model_compress_range(const EncParams* Pin, const uint8_t* input, uint
     w.put(6, 6);
     w.pos = (w.pos + 7) & ~7ull;
   }
-  return (size_t)((w.pos + 7) >> 3);
+  return w.pos;
 }
 
 }  // extern "C"
