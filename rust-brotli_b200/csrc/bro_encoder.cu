@@ -59,7 +59,7 @@ constexpr uint32_t kPad = 512;                 // zero bytes after the input
 constexpr uint32_t kChunk = BRO_CHUNK_BYTES;   // bytes per pipeline pass (one sort batch for lgwin <= 22)
 constexpr uint32_t kBatchMax = 1u << 25;       // positions per sort batch (25-bit packed positions)
 constexpr uint32_t kLookahead = 4096;          // input bytes past a chunk's end that must be resident before it runs
-constexpr int kMaxLanes = 2;
+constexpr int kMaxLanes = 6;
 
 struct EventPool {
   std::vector<cudaEvent_t> ev;
@@ -107,7 +107,7 @@ struct B200Encoder {
   // configuration knobs (tests flip these)
   uint32_t unit = 4096, mb_units = 1024, lcap = 64;
   int use_rle_opt = 1, split = 1, ctx_model = 1;
-  int num_lanes = kMaxLanes;
+  int num_lanes = 4;
   Lane lanes[kMaxLanes];
   cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams
   DevBuf d_data, d_lut, d_out, d_total;          // d_total: [0] running bit position, [1 + k] position after chunk k
@@ -371,7 +371,8 @@ struct B200Encoder {
       ma.max_backward = P.max_backward;
       const size_t smem = (size_t)(MATCH_THREADS + P.depth) * 6 * 4;
       mark(L, B200_ST_MATCH);
-      k_match<<<(count + MATCH_THREADS - 1) / MATCH_THREADS, MATCH_THREADS, smem, stream>>>(ma);
+      if (P.depth >= 64) k_match<true><<<(count + MATCH_THREADS - 1) / MATCH_THREADS, MATCH_THREADS, smem, stream>>>(ma);
+      else k_match<false><<<(count + MATCH_THREADS - 1) / MATCH_THREADS, MATCH_THREADS, smem, stream>>>(ma);
       launches += 1;
     }
     mark(L, B200_ST_PARSE);

@@ -332,7 +332,11 @@ __device__ __forceinline__ void load16_unaligned(const uint8_t* p, uint32_t* w) 
   w[3] = __funnelshift_r(a3, a4, sh);
 }
 
-// dynamic shared memory: (MATCH_THREADS + depth) entries x 6 words
+// dynamic shared memory: (MATCH_THREADS + depth) entries x 6 words.
+// PREFILTER (deep buckets, q7..q9): a farther candidate only wins if it is strictly longer, so it is rejected on the byte at
+// index best_len before the full comparison (the reference's cur[best_len] != prev[best_len] test, mod.rs:1765-1773);
+// same result, and for the shallow q5/q6 buckets the extra branch costs more than it saves.
+template <bool PREFILTER>
 __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
   extern __shared__ uint32_t smem[];
   const uint32_t E = MATCH_THREADS + (uint32_t)a.depth;
@@ -381,6 +385,13 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
         const uint32_t ci = i - 1u - cbase - c;
         const uint32_t backward = prel - s_pos[ci];
         if (backward > max_backward) { done = true; break; }
+        if (PREFILTER && best_len >= 4) {
+          if (best_len < 16) {
+            const uint32_t wsel = (2u + (best_len >> 2)) * E;
+            const uint32_t xb = smem[wsel + ci] ^ smem[wsel + i];
+            if ((xb >> ((best_len & 3u) * 8u)) & 0xFFu) continue;
+          } else if (a.data[p + best_len] != a.data[p - backward + best_len]) continue;
+        }
         uint32_t len;
         uint32_t x = s_d1[ci] ^ m1;
         if (x) len = 4 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
