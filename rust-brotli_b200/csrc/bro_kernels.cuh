@@ -260,7 +260,19 @@ __global__ void __launch_bounds__(SORT_THREADS, 6) k_sort_scatter(SortArgs a) {
       }
     }
     s_word[e] = w;
+#ifdef SORT_USE_MATCH_ANY
     const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+#else
+    // lanes with the same digit, from 9 ballots (MATCH.ANY measured slower: it goes through the MIO queue)
+    uint32_t peers = __ballot_sync(0xffffffffu, valid);
+    if (!valid) peers = ~peers;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const bool bit = (digit >> b) & 1u;
+      const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? bal : ~bal;
+    }
+#endif
     const uint32_t rank_in_round = __popc(peers & ((1u << lane) - 1u));
     uint32_t old = 0;
     if (valid) old = wc[wid][digit];
@@ -613,6 +625,7 @@ __device__ __forceinline__ uint32_t parse_unit_warp4(const EncParams& P, const u
   const uint32_t FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t j_lane = lane >> 2, i_lane = lane & 3;
+  const bool il1 = (lane & 1u) != 0, il2 = (lane & 2u) != 0;
   int32_t dc0 = 0x3fffffff, dc1 = 0x3fffffff, dc2 = 0x3fffffff, dc3 = 0x3fffffff;
   const uint32_t htl = P.hash_type == 6 ? 8u : 4u;
   const uint32_t window = 64u;  // quality < 9 on this path
@@ -631,7 +644,7 @@ __device__ __forceinline__ uint32_t parse_unit_warp4(const EncParams& P, const u
     const uint32_t maxl = p_ok ? uend - p : 0u;
     uint32_t clen = 0, cdist = 0, key = 0;
     if (p_ok) {
-      const int32_t back = i_lane == 0 ? dc0 : (i_lane == 1 ? dc1 : (i_lane == 2 ? dc2 : dc3));
+      const int32_t back = il2 ? (il1 ? dc3 : dc2) : (il1 ? dc1 : dc0);  // selects, not branches
       const uint32_t mb = near_start ? bmin(p + P.abs_base, P.max_backward) : P.max_backward;
       if (back > 0 && (uint32_t)back <= mb) {
         const uint64_t x = ldu64(data + p) ^ ldu64(data + p - back);
@@ -728,11 +741,7 @@ __device__ __forceinline__ uint32_t parse_unit_warp4(const EncParams& P, const u
       }
       arh = pos + 2 * m_len + window;
       if ((int32_t)m_dist != dc0) { dc3 = dc2; dc2 = dc1; dc1 = dc0; dc0 = (int32_t)m_dist; }
-      if (lane == 0) {
-        out[ncmd].insert_len = insert_len;
-        out[ncmd].copy_len = m_len;
-        out[ncmd].distance = m_dist;
-      }
+      if (lane < 3) reinterpret_cast<uint32_t*>(out + ncmd)[lane] = lane == 0 ? insert_len : (lane == 1 ? m_len : m_dist);  // one store
       ++ncmd;
       insert_len = 0;
       copied += m_len;
