@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libbrotli_b200.so")
 SOURCES = ["bro_encoder.cu", "bro_capi.cu"]
 DEPS = ["bro_common.cuh", "bro_huffman.cuh", "bro_meta.cuh", "bro_parse.cuh", "bro_split.cuh", "bro_finalize.cuh",
-        "bro_kernels.cuh", "bro_encoder.h"]
+        "bro_kernels.cuh", "bro_encoder.h", "bro_dict.cuh", "bro_dict_data.inc"]
 
 
 def needs_build():
@@ -21,6 +21,9 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    inc = os.path.join(CSRC, "bro_dict_data.inc")
+    if not os.path.exists(inc):  # generated: RFC 7932 dictionary (from the system libbrotlicommon) + our hash table
+        subprocess.check_call([sys.executable, os.path.join(HERE, "gen_dict.py")])
     if not force and not needs_build():
         return OUT
     objs = []

@@ -17,6 +17,7 @@
 
 #include "bro_kernels.cuh"
 #include "bro_encoder.h"
+#include "bro_dict_data.inc"  // generated at build time by gen_dict.py: kDictData, kDictHash
 
 using namespace bro;
 
@@ -106,10 +107,11 @@ struct B200Encoder {
   bool ok = false;
   // configuration knobs (tests flip these)
   uint32_t unit = 4096, mb_units = 1024, lcap = 64;
-  int use_rle_opt = 1, split = 1, ctx_model = 1;
+  int use_rle_opt = 1, split = 1, ctx_model = 1, use_dict = 1;
   int num_lanes = 4;
   Lane lanes[kMaxLanes];
   cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams
+  DevBuf d_dict_words, d_dict_hash;
   DevBuf d_data, d_lut, d_out, d_total;          // d_total: [0] running bit position, [1 + k] position after chunk k
   uint64_t* h_total = nullptr;                   // pinned mirror of d_total[1 + k]
   size_t h_total_cap = 0;
@@ -130,6 +132,10 @@ struct B200Encoder {
     lut[0] = 0;
     for (uint32_t i = 1; i < 65536; ++i) lut[i] = (uint32_t)llround(std::log2((double)i) * 65536.0);
     CUDA_OK(cudaMemcpy(d_lut.p, lut.data(), 65536 * 4, cudaMemcpyHostToDevice));
+    if (!d_dict_words.ensure(sizeof(kDictData) + 64) || !d_dict_hash.ensure(sizeof(kDictHash))) return false;
+    CUDA_OK(cudaMemset(d_dict_words.p, 0, sizeof(kDictData) + 64));
+    CUDA_OK(cudaMemcpy(d_dict_words.p, kDictData, sizeof(kDictData), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(d_dict_hash.p, kDictHash, sizeof(kDictHash), cudaMemcpyHostToDevice));
     CUDA_OK(cudaDeviceSetLimit(cudaLimitStackSize, 4096));
     for (int i = 0; i < B200_NUM_STAGES; ++i) stage_ms[i] = 0;
     ok = true;
@@ -139,7 +145,7 @@ struct B200Encoder {
     cudaSetDevice(device);
     cudaDeviceSynchronize();
     for (auto& L : lanes) L.release();
-    DevBuf* all[] = {&d_data, &d_lut, &d_out, &d_total};
+    DevBuf* all[] = {&d_data, &d_lut, &d_out, &d_total, &d_dict_words, &d_dict_hash};
     for (auto* b : all) b->release();
     if (h_total) cudaFreeHost(h_total);
     sync_events.destroy();
@@ -185,6 +191,7 @@ struct B200Encoder {
     P->use_rle_opt = use_rle_opt;
     P->split = split;
     P->ctx_model = ctx_model;
+    P->use_dict = use_dict;
   }
 
   // device buffers of lane L for one chunk of `c` bytes
@@ -243,6 +250,8 @@ struct B200Encoder {
     if (!L.d_digit.ensure(512 * 4)) return false;
     // wire pointers
     W->lut = d_lut.as<uint32_t>();
+    W->dict.words = d_dict_words.as<uint8_t>();
+    W->dict.hash = d_dict_hash.as<uint16_t>();
     W->best = L.d_best.as<uint32_t>();
     W->raw = L.d_raw.as<RawCmd>();
     uint32_t* up = L.d_unit.as<uint32_t>();
@@ -456,6 +465,7 @@ int b200_encoder_set_option(B200Encoder* e, int option, uint32_t value) {
     case B200_OPT_SPLIT: e->split = (int)value; return 1;
     case B200_OPT_CTX_MODEL: e->ctx_model = (int)value; return 1;
     case B200_OPT_TIMING: e->timing = value != 0; return 1;
+    case B200_OPT_DICT: e->use_dict = (int)value; return 1;
     case B200_OPT_LANES: e->num_lanes = value < 1 ? 1 : (value > (uint32_t)kMaxLanes ? kMaxLanes : (int)value); return 1;
   }
   return 0;

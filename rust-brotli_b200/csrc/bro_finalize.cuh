@@ -22,7 +22,7 @@ namespace bro {
 
 struct GCmd {  // final command record in device memory (32 bytes)
   uint32_t insert_len;
-  uint32_t copy_len;
+  uint32_t copy_len;    // packed like RawCmd::copy_len (bro_dict.cuh): bytes covered | word-length delta | dictionary flag
   uint32_t dist_extra;
   uint16_t cmd_prefix;
   uint16_t dist_prefix;
@@ -32,7 +32,7 @@ struct GCmd {  // final command record in device memory (32 bytes)
   uint32_t pad;       // owning parse unit (device: dist_idx is unit-relative until unit_dist_off[pad] is added)
   BRO_HD Cmd as_cmd() const {
     Cmd c;
-    c.insert_len = insert_len; c.copy_len = copy_len; c.dist_extra = dist_extra;
+    c.insert_len = insert_len; c.copy_len = len_coded(copy_len); c.dist_extra = dist_extra;  // Cmd carries the coded length
     c.cmd_prefix = cmd_prefix; c.dist_prefix = dist_prefix;
     return c;
   }
@@ -60,10 +60,10 @@ BRO_HD uint32_t unit_carry_in(const UnitView& V, uint32_t u0, uint32_t u) {
 BRO_HD bool unit_absorbed(const UnitView& V, uint32_t u0, uint32_t u) {
   if (u == u0 || V.ncmd[u] == 0) return false;
   const RawCmd& f = V.raw[(size_t)u * V.cu];
-  if (f.insert_len != 0) return false;
+  if (f.insert_len != 0 || len_is_dict(f.copy_len)) return false;
   if (V.tail[u - 1] != 0 || V.ncmd[u - 1] == 0) return false;
   const RawCmd& l = V.raw[(size_t)(u - 1) * V.cu + V.ncmd[u - 1] - 1];
-  return l.distance == f.distance;
+  return l.distance == f.distance && !len_is_dict(l.copy_len);
 }
 // number of final commands a unit contributes to its metablock (u1 = one past the metablock's last unit)
 BRO_HD uint32_t unit_final_ncmd(const UnitView& V, uint32_t u0, uint32_t u1, uint32_t u) {
@@ -94,6 +94,7 @@ BRO_HD_NOINLINE uint32_t finalize_unit(const UnitView& V, uint32_t u0, uint32_t 
       --v;
       for (uint32_t i = V.ncmd[v]; i > 0 && k < 4;) {
         --i;
+        if (len_is_dict(V.raw[(size_t)v * V.cu + i].copy_len)) continue;  // not part of the distance sequence
         uint32_t d = V.raw[(size_t)v * V.cu + i].distance;
         if (d != last) { dc[k++] = (int32_t)d; last = d; }
       }
@@ -102,6 +103,7 @@ BRO_HD_NOINLINE uint32_t finalize_unit(const UnitView& V, uint32_t u0, uint32_t 
   uint32_t nout = 0, ndist = 0, lit_idx = lit_base, pos = ustart;
   for (uint32_t i = 0; i < nraw; ++i) {
     uint32_t ins = rc[i].insert_len, len = rc[i].copy_len, dist = rc[i].distance;
+    const bool is_dict = len_is_dict(len);
     if (i == 0) {
       if (absorbed) {  // emitted by the owner in an earlier unit
         pos += len;
@@ -115,8 +117,8 @@ BRO_HD_NOINLINE uint32_t finalize_unit(const UnitView& V, uint32_t u0, uint32_t 
         if (!(V.ncmd[v] == 1 && V.tail[v] == 0)) break;
       }
     }
-    uint32_t code = compute_distance_code(dist, dc);
-    if (code != 0) { dc[3] = dc[2]; dc[2] = dc[1]; dc[1] = dc[0]; dc[0] = (int32_t)dist; }
+    uint32_t code = is_dict ? dist + 15u : compute_distance_code(dist, dc);
+    if (code != 0 && !is_dict) { dc[3] = dc[2]; dc[2] = dc[1]; dc[1] = dc[0]; dc[0] = (int32_t)dist; }
     uint32_t sym_nbits, extra;
     prefix_encode_copy_distance(code, &sym_nbits, &extra);
     GCmd g;
@@ -124,7 +126,7 @@ BRO_HD_NOINLINE uint32_t finalize_unit(const UnitView& V, uint32_t u0, uint32_t 
     g.copy_len = len;
     g.dist_extra = extra;
     g.dist_prefix = (uint16_t)sym_nbits;
-    g.cmd_prefix = (uint16_t)combine_length_codes(insert_length_code(ins), copy_length_code(len), code == 0);
+    g.cmd_prefix = (uint16_t)combine_length_codes(insert_length_code(ins), copy_length_code(len_coded(len)), code == 0);
     g.lit_idx = lit_idx - ((i == 0) ? carry : 0u);
     g.dist_idx = ndist;
     g.pos = pos - ((i == 0) ? carry : 0u);
@@ -132,7 +134,7 @@ BRO_HD_NOINLINE uint32_t finalize_unit(const UnitView& V, uint32_t u0, uint32_t 
     if (g.cmd_prefix >= 128) ++ndist;
     out[nout++] = g;
     lit_idx += rc[i].insert_len;
-    pos += rc[i].insert_len + rc[i].copy_len;
+    pos += rc[i].insert_len + len_bytes(rc[i].copy_len);
   }
   if (u + 1 == u1) {
     uint32_t carry_out = V.tail[u] + (nraw == 0 ? carry : 0u);

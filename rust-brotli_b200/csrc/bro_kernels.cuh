@@ -55,6 +55,7 @@ struct Workspace {
   // input
   const uint8_t* data;  // padded with >= 320 zero bytes
   const uint32_t* lut;
+  DictView dict;        // static dictionary words + hash table (device copies)
   EncParams P;
   uint32_t num_units, num_mb;
   // match
@@ -470,13 +471,12 @@ __device__ __forceinline__ uint32_t warp_lcp_ext(const uint8_t* cur, uint32_t ba
 template <int NL>
 __device__ __forceinline__ uint32_t parse_unit_warp(const EncParams& P, const uint8_t* data, const uint32_t* best,
                                                     uint32_t ustart, uint32_t uend, RawCmd* out, uint32_t* tail,
-                                                    uint32_t* ncopy) {
+                                                    uint32_t* ncopy, const DictView* D, int32_t* dc) {
   constexpr int G = 32 / NL;
   constexpr uint32_t CAPA = 8;  // bytes compared per probe in the parallel phase
   const uint32_t FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t j_lane = lane / NL, i_lane = lane % NL;
-  int32_t dc[4] = {0x3fffffff, 0x3fffffff, 0x3fffffff, 0x3fffffff};
   const uint32_t htl = P.hash_type == 6 ? 8u : 4u;
   const uint32_t window = P.quality < 9 ? 64u : 512u;
   const int n_last = P.n_last;
@@ -542,6 +542,7 @@ __device__ __forceinline__ uint32_t parse_unit_warp(const EncParams& P, const ui
         }
       }
       o->len = best_len; o->dist = best_dist; o->score = best_score;
+      if (!found && D) found = dict_search(*D, P.hash_type, data + p, max_len, max_backward_at(p), o);  // warp-uniform
       return found;
     };
 
@@ -581,17 +582,18 @@ __device__ __forceinline__ uint32_t parse_unit_warp(const EncParams& P, const ui
         }
       }
       // accept m at pos
-      arh = pos + 2 * m.len + window;
-      if ((int32_t)m.dist != dc[0]) { dc[3] = dc[2]; dc[2] = dc[1]; dc[1] = dc[0]; dc[0] = (int32_t)m.dist; }
-      if (lane == 0) {
+      const uint32_t mlen = len_bytes(m.len);
+      arh = pos + 2 * mlen + window;
+      if (!len_is_dict(m.len) && (int32_t)m.dist != dc[0]) { dc[3] = dc[2]; dc[2] = dc[1]; dc[1] = dc[0]; dc[0] = (int32_t)m.dist; }
+      if (out && lane == 0) {
         out[ncmd].insert_len = insert_len;
         out[ncmd].copy_len = m.len;
         out[ncmd].distance = m.dist;
       }
       ++ncmd;
       insert_len = 0;
-      copied += m.len;
-      pos += m.len;
+      copied += mlen;
+      pos += mlen;
       have_m = false;
       break;  // the distance cache changed: new window
     }
@@ -619,14 +621,14 @@ __device__ __forceinline__ uint32_t lane_lcp_ext(const uint8_t* cur, uint32_t ba
 // walk only reads finished (found, len, dist, score) tuples: ballots locate the next match, shuffles fetch it.
 __device__ __forceinline__ uint32_t parse_unit_warp4(const EncParams& P, const uint8_t* data, const uint32_t* best,
                                                      uint32_t ustart, uint32_t uend, RawCmd* out, uint32_t* tail,
-                                                     uint32_t* ncopy) {
+                                                     uint32_t* ncopy, const DictView* D, int32_t* dc) {
   constexpr int G = 8;
   constexpr uint32_t CAPA = 8;
   const uint32_t FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t j_lane = lane >> 2, i_lane = lane & 3;
   const bool il1 = (lane & 1u) != 0, il2 = (lane & 2u) != 0;
-  int32_t dc0 = 0x3fffffff, dc1 = 0x3fffffff, dc2 = 0x3fffffff, dc3 = 0x3fffffff;
+  int32_t dc0 = dc[0], dc1 = dc[1], dc2 = dc[2], dc3 = dc[3];
   const uint32_t htl = P.hash_type == 6 ? 8u : 4u;
   const uint32_t window = 64u;  // quality < 9 on this path
   uint32_t pos = ustart, insert_len = 0, ncmd = 0, copied = 0;
@@ -681,6 +683,19 @@ __device__ __forceinline__ uint32_t parse_unit_warp4(const EncParams& P, const u
           if (f_score < score) { f_score = score; f_len = len; f_dist = bdist; f_found = true; }
         }
       }
+    }
+    if (D) {  // unit gate open (warp-uniform): lane 4j+1 probes the dictionary for position j, lane 4j takes it if nothing else matched
+      Match dm;
+      dm.len = dm.dist = 0;
+      dm.score = BRO_MIN_SCORE;
+      bool dfound = false;
+      if (p_ok && i_lane == 1) {
+        const uint32_t mb = near_start ? bmin(p + P.abs_base, P.max_backward) : P.max_backward;
+        dfound = dict_search(*D, 5, data + p, maxl, mb, &dm);
+      }
+      const int src = (int)((lane & ~3u) + 1u);
+      const uint32_t dl = __shfl_sync(FULL, dfound ? dm.len : 0u, src), dd = __shfl_sync(FULL, dm.dist, src), ds = __shfl_sync(FULL, dm.score, src);
+      if (i_lane == 0 && !f_found && dl != 0) { f_found = true; f_len = dl; f_dist = dd; f_score = ds; }
     }
     // lane 4*j now holds the finished result of position wbase + j
     uint32_t found8 = __ballot_sync(FULL, f_found && i_lane == 0);  // bits 0,4,8,.. -> compress to bits 0..7
@@ -739,13 +754,14 @@ __device__ __forceinline__ uint32_t parse_unit_warp4(const EncParams& P, const u
           if (++delayed < 4 && pos + htl < uend) continue;
         }
       }
-      arh = pos + 2 * m_len + window;
-      if ((int32_t)m_dist != dc0) { dc3 = dc2; dc2 = dc1; dc1 = dc0; dc0 = (int32_t)m_dist; }
-      if (lane < 3) reinterpret_cast<uint32_t*>(out + ncmd)[lane] = lane == 0 ? insert_len : (lane == 1 ? m_len : m_dist);  // one store
+      const uint32_t m_bytes = len_bytes(m_len);
+      arh = pos + 2 * m_bytes + window;
+      if (!len_is_dict(m_len) && (int32_t)m_dist != dc0) { dc3 = dc2; dc2 = dc1; dc1 = dc0; dc0 = (int32_t)m_dist; }
+      if (out && lane < 3) reinterpret_cast<uint32_t*>(out + ncmd)[lane] = lane == 0 ? insert_len : (lane == 1 ? m_len : m_dist);  // one store
       ++ncmd;
       insert_len = 0;
-      copied += m_len;
-      pos += m_len;
+      copied += m_bytes;
+      pos += m_bytes;
       have_m = false;
       break;
     }
@@ -753,6 +769,7 @@ __device__ __forceinline__ uint32_t parse_unit_warp4(const EncParams& P, const u
   insert_len += uend - pos;
   *tail = insert_len;
   *ncopy = copied;
+  dc[0] = dc0; dc[1] = dc1; dc[2] = dc2; dc[3] = dc3;
   return ncmd;
 }
 
@@ -764,9 +781,28 @@ __global__ void __launch_bounds__(PARSE_WARPS * 32) k_parse(Workspace W) {
   const uint32_t s = u * P.unit, e = bmin(P.n, s + P.unit);
   uint32_t tail, ncopy, ncmd;
   const uint32_t cu = P.unit / 2 + 1;
-  if (P.n_last == 4 && P.hash_type != 9) ncmd = parse_unit_warp4(P, W.data, W.best, s, e, W.raw + (size_t)u * cu, &tail, &ncopy);
-  else if (P.n_last <= 4) ncmd = parse_unit_warp<4>(P, W.data, W.best, s, e, W.raw + (size_t)u * cu, &tail, &ncopy);
-  else ncmd = parse_unit_warp<16>(P, W.data, W.best, s, e, W.raw + (size_t)u * cu, &tail, &ncopy);
+  // dictionary gate of the unit (dict_unit_gate of bro_dict.cuh, two samples per lane)
+  bool gate = false;
+  if (P.use_dict) {
+    const uint32_t lane = threadIdx.x & 31;
+    gate = __any_sync(0xffffffffu, dict_gate_sample(W.dict, P.hash_type, W.data, s, e, lane) ||
+                                       dict_gate_sample(W.dict, P.hash_type, W.data, s, e, lane + 32));
+  }
+  const DictView* D = gate ? &W.dict : nullptr;
+  // phase 0: warm-up over the BRO_WARMUP_BYTES in front of the unit (commands discarded, only the distance cache is kept);
+  // phase 1: the unit itself.  One loop body so that the parse code is instantiated once.
+  int32_t dc[4] = {0x3fffffff, 0x3fffffff, 0x3fffffff, 0x3fffffff};
+  const bool warm = (u % P.mb_units) != 0 && s >= BRO_WARMUP_BYTES;
+  RawCmd* const out = W.raw + (size_t)u * cu;
+  ncmd = 0;
+  for (int phase = warm ? 0 : 1; phase < 2; ++phase) {
+    const uint32_t rs = phase ? s : s - BRO_WARMUP_BYTES, re = phase ? e : s;
+    RawCmd* const o = phase ? out : nullptr;
+    const DictView* const Dp = phase ? D : nullptr;
+    if (P.n_last == 4 && P.hash_type != 9) ncmd = parse_unit_warp4(P, W.data, W.best, rs, re, o, &tail, &ncopy, Dp, dc);
+    else if (P.n_last <= 4) ncmd = parse_unit_warp<4>(P, W.data, W.best, rs, re, o, &tail, &ncopy, Dp, dc);
+    else ncmd = parse_unit_warp<16>(P, W.data, W.best, rs, re, o, &tail, &ncopy, Dp, dc);
+  }
   if ((threadIdx.x & 31) == 0) {
     W.unit_ncmd[u] = ncmd;
     W.unit_tail[u] = tail;
@@ -856,6 +892,7 @@ __device__ __forceinline__ void lookback_cache(const UnitView& V, uint32_t u0, u
   for (;;) {
     while (idx > 0 && k < 4) {
       --idx;
+      if (len_is_dict(V.raw[(size_t)v * V.cu + idx].copy_len)) continue;  // not part of the distance sequence
       const uint32_t d = V.raw[(size_t)v * V.cu + idx].distance;
       if (d != last) { dc[k++] = (int32_t)d; last = d; }
     }
@@ -897,13 +934,14 @@ __global__ void __launch_bounds__(PARSE_WARPS * 32) k_fin_write(Workspace W) {
     uint32_t ins_r = 0, len_r = 0, dist = 0;
     if (act) { ins_r = rc[i].insert_len; len_r = rc[i].copy_len; dist = rc[i].distance; }
     // exclusive warp scans of literals and of covered bytes
-    uint32_t sl = ins_r, sp = ins_r + len_r;
+    const uint32_t bytes_r = len_bytes(len_r);
+    uint32_t sl = ins_r, sp = ins_r + bytes_r;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t a1 = __shfl_up_sync(FULL, sl, o), a2 = __shfl_up_sync(FULL, sp, o);
       if (lane >= (uint32_t)o) { sl += a1; sp += a2; }
     }
-    const uint32_t lit_before = lit_run + sl - ins_r, pos_before = pos_run + sp - (ins_r + len_r);
+    const uint32_t lit_before = lit_run + sl - ins_r, pos_before = pos_run + sp - (ins_r + bytes_r);
     const bool emit = act && !(i == 0 && absorbed);
     uint32_t cmd_prefix = 0, sym_nbits = 0, extra = 0, ins = ins_r, len = len_r;
     if (emit) {
@@ -911,9 +949,9 @@ __global__ void __launch_bounds__(PARSE_WARPS * 32) k_fin_write(Workspace W) {
       if (i + 1 == nraw) len += cont;
       int32_t dc[4];
       lookback_cache(V, u0, u, i, dc);
-      const uint32_t code = compute_distance_code(dist, dc);
+      const uint32_t code = len_is_dict(len) ? dist + 15u : compute_distance_code(dist, dc);
       prefix_encode_copy_distance(code, &sym_nbits, &extra);
-      cmd_prefix = combine_length_codes(insert_length_code(ins), copy_length_code(len), code == 0);
+      cmd_prefix = combine_length_codes(insert_length_code(ins), copy_length_code(len_coded(len)), code == 0);
     }
     const uint32_t hd = __ballot_sync(FULL, emit && cmd_prefix >= 128);
     if (emit) {

@@ -36,8 +36,8 @@ def test_config1_alice29_q5_w20(encoder, oracle):
     assert sys_decompress(c, len(d)) == d
     ref, _ = oracle.compress(d, 5, 20)
     assert len(c) <= len(ref) * 1.005
-    # vs Google's C encoder (which also matches static-dictionary words, not yet on this path): within 1 %
-    assert len(c) <= len(sys_compress(d, 5, 20)) * 1.01
+    # vs Google's C encoder (the code the reference is a port of; it also matches static-dictionary words): within 0.5 %
+    assert len(c) <= len(sys_compress(d, 5, 20)) * 1.005
 
 
 def test_match_stage_equals_model(encoder, model):
@@ -88,6 +88,32 @@ def test_multi_chunk_stream_equals_model(encoder, model):
         c = encoder.compress(d, 5, 22)
         assert c == ref, "lanes=%d" % lanes
     assert sys_decompress(ref, len(d)) == d
+
+
+def test_structured_logs_size_parity(encoder, oracle):
+    """Record-structured JSON logs lean on the distance cache: the warm-up in front of every parse unit keeps the size
+    within +0.5 % of the reference restatement (it was +1.4 % with units that start from an unknown cache)."""
+    from tools import datagen
+    d = datagen.json_logs(4_000_000)
+    for q in (5, 9):
+        c = encoder.compress(d, q, 22)
+        assert sys_decompress(c, len(d)) == d
+        assert len(c) <= len(oracle.compress(d, q, 22)[0]) * 1.005
+
+
+def test_static_dictionary_toggle(encoder, model):
+    """Static-dictionary references (distances beyond the window) decode, equal the model, and pay off on English text."""
+    import rust_brotli_b200 as rb
+    d = golden_bytes("asyoulik.txt")
+    on = encoder.compress(d, 5, 22)
+    encoder.set_option(rb._native.OPT_DICT, 0)
+    try:
+        off = encoder.compress(d, 5, 22)
+    finally:
+        encoder.set_option(rb._native.OPT_DICT, 1)
+    assert sys_decompress(on, len(d)) == d and sys_decompress(off, len(d)) == d
+    assert on == model.compress(d, 5, 22)[0] and off == model.compress(d, 5, 22, use_dict=0)[0]
+    assert len(on) < len(off)
 
 
 def test_long_literal_runs(encoder, model):
