@@ -33,10 +33,11 @@ BRO_HD uint32_t dict_size_bits(uint32_t len) {  // NDBITS, RFC 7932 section 8
   const uint64_t hi = 0x0000000556677877ull;   // lengths 16..31
   return (uint32_t)(((len < 16 ? lo : hi) >> ((len & 15u) * 4u)) & 0xFu);
 }
-BRO_HD uint32_t dict_offset(uint32_t len) {  // offset of the first word of this length
-  uint32_t off = 0;
-  for (uint32_t l = 4; l < len; ++l) off += l << dict_size_bits(l);
-  return off;
+BRO_HD uint32_t dict_offset(uint32_t len) {  // offset of the first word of this length = sum over l < len of l << NDBITS[l]
+  static constexpr uint32_t kOff[32] = {0, 0, 0, 0, 0, 4096, 9216, 21504, 35840, 44032, 53248, 63488, 74752, 87040, 93696, 100864,
+                                        104704, 106752, 108928, 113536, 115968, 118528, 119872, 121280, 122016, 122784, 122784,
+                                        122784, 122784, 122784, 122784, 122784};
+  return kOff[len & 31u];
 }
 BRO_HD uint32_t dict_omit_last_transform(uint32_t cut) {  // RFC 7932 appendix B: identity, OmitLast1..9
   switch (cut) {
@@ -60,7 +61,8 @@ BRO_HD bool dict_search(const DictView& D, int hash_type, const uint8_t* cur, ui
     const uint8_t* w = D.words + dict_offset(len) + len * idx;
     uint32_t ml = 0;
     while (ml < len && cur[ml] == w[ml]) ++ml;
-    if (ml + 10u <= len || ml == 0) continue;
+    if (ml + 10u <= len || ml < 4) continue;  // ml < 4: the slot was reached through a hash collision (the reference would accept
+                                              // such a 1..3 byte OmitLast match when the window is tiny; not worth a byte-wise path)
     const uint32_t backward = max_backward_here + 1u + idx + (dict_omit_last_transform(len - ml) << dict_size_bits(len));
     if (backward > 0x3FFFFFCu) continue;
     const uint32_t score = score_regular(hash_type, ml, backward);

@@ -684,17 +684,41 @@ __device__ __forceinline__ uint32_t parse_unit_warp4(const EncParams& P, const u
         }
       }
     }
-    if (D) {  // unit gate open (warp-uniform): lane 4j+1 probes the dictionary for position j, lane 4j takes it if nothing else matched
-      Match dm;
-      dm.len = dm.dist = 0;
-      dm.score = BRO_MIN_SCORE;
-      bool dfound = false;
-      if (p_ok && i_lane == 1) {
-        const uint32_t mb = near_start ? bmin(p + P.abs_base, P.max_backward) : P.max_backward;
-        dfound = dict_search(*D, 5, data + p, maxl, mb, &dm);
+    if (D) {  // unit gate open (warp-uniform): lanes 4j+1 / 4j+2 probe the two table slots of position j (dict_search of
+              // bro_dict.cuh, one slot per lane, 8-byte compares); lane 4j takes the result if nothing else matched
+      uint32_t d_len = 0, d_dist = 0, d_score = 0;
+      if (p_ok && (i_lane == 1 || i_lane == 2)) {
+        const uint64_t cw = ldu64(data + p);
+        const uint32_t item = D->hash[(dict_hash14((uint32_t)cw) << 1) + (i_lane - 1u)];
+        const uint32_t wl = item & 31u, idx = item >> 5;
+        if (item != 0 && wl <= maxl) {
+          const uint8_t* w = D->words + dict_offset(wl) + wl * idx;
+          uint32_t ml = 0;
+          uint64_t x = cw ^ ldu64(w);
+          if ((uint32_t)x == 0) {  // the 4 hashed bytes agree (anything else is a hash collision)
+            ml = x ? ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : 8u;
+            while (ml == 8u || ml == 16u) {
+              if (ml >= wl) break;
+              x = ldu64(data + p + ml) ^ ldu64(w + ml);
+              ml += x ? ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : 8u;
+              if (x) break;
+            }
+            ml = bmin(ml, wl);
+          }
+          if (ml >= 4u && ml + 10u > wl) {
+            const uint32_t mb = near_start ? bmin(p + P.abs_base, P.max_backward) : P.max_backward;
+            const uint32_t backward = mb + 1u + idx + (dict_omit_last_transform(wl - ml) << dict_size_bits(wl));
+            const uint32_t score = score_regular(5, ml, backward);
+            if (backward <= 0x3FFFFFCu && score >= BRO_MIN_SCORE) { d_len = pack_dict_len(ml, wl); d_dist = backward; d_score = score; }
+          }
+        }
       }
-      const int src = (int)((lane & ~3u) + 1u);
-      const uint32_t dl = __shfl_sync(FULL, dfound ? dm.len : 0u, src), dd = __shfl_sync(FULL, dm.dist, src), ds = __shfl_sync(FULL, dm.score, src);
+      const int s1 = (int)((lane & ~3u) + 1u), s2 = s1 + 1;
+      const uint32_t l1 = __shfl_sync(FULL, d_len, s1), l2 = __shfl_sync(FULL, d_len, s2);
+      const uint32_t sc1 = __shfl_sync(FULL, d_score, s1), sc2 = __shfl_sync(FULL, d_score, s2);
+      const bool take2 = l2 != 0 && (l1 == 0 || sc2 >= sc1);  // the later slot wins ties, as in the sequential search
+      const uint32_t dd = __shfl_sync(FULL, d_dist, take2 ? s2 : s1);
+      const uint32_t dl = take2 ? l2 : l1, ds = take2 ? sc2 : sc1;
       if (i_lane == 0 && !f_found && dl != 0) { f_found = true; f_len = dl; f_dist = dd; f_score = ds; }
     }
     // lane 4*j now holds the finished result of position wbase + j
