@@ -5,10 +5,9 @@
 // if at least len - 9 of its bytes match (identity or one of the nine "omit last N" transforms), encode it as a distance
 // beyond the window: max_backward + 1 + word_index + (transform_id << size_bits[len]).
 //
-// Differences, both forced by parallelism: the hash table is this library's own (gen_dict.py), and the reference's
-// running lookups/matches counter (a sequential, stream-global heuristic that switches the search off on input without
-// dictionary words) is replaced by a per-unit gate that is a pure function of the unit's bytes: 64 sample positions
-// are probed, the dictionary is searched in this unit iff one of them hits.
+// Differences: the hash table is this library's own (gen_dict.py), and the reference's running lookups/matches counter (a
+// sequential, stream-global heuristic that switches the search off on input without dictionary words) has no parallel
+// equivalent and is dropped -- the lookup is done by the position-parallel match kernel where it costs little.
 //
 // Included by bro_parse.cuh (after Match / score_regular, before find_match); do not include directly.
 #pragma once
@@ -47,11 +46,20 @@ BRO_HD uint32_t dict_omit_last_transform(uint32_t cut) {  // RFC 7932 appendix B
 }
 BRO_HD uint32_t dict_hash14(uint32_t w) { return (w * 0x1e35a7bdu) >> 18; }
 
-// Tries the two slots of the position's bucket.  m->score is the score to reach (BRO_MIN_SCORE when nothing was found);
-// on success m->len = pack_dict_len(bytes matched, word length), m->dist = the dictionary distance.
-BRO_HD bool dict_search(const DictView& D, int hash_type, const uint8_t* cur, uint32_t max_len, uint32_t max_backward_here,
-                        Match* m) {
-  bool found = false;
+// The dictionary candidate of a position is found by the match stage (only where the bucket search found nothing) and
+// travels to the parse in best[p]:
+//   bucket match : dist << 8 | len            (len 4..64, bit 7 clear)
+//   dictionary   : cut << 26 | word_id << 8 | 0x80 | bytes matched      word_id = word_index + (transform << NDBITS[len])
+// The parse uses it only if the distance cache gave nothing either (mod.rs:1797 "if !is_match_found").
+#define BRO_BEST_DICT 0x80u
+BRO_HD uint32_t best_pack_dict(uint32_t ml, uint32_t wl, uint32_t idx) {
+  const uint32_t word_id = idx + (dict_omit_last_transform(wl - ml) << dict_size_bits(wl));
+  return ((wl - ml) << 26) | (word_id << 8) | BRO_BEST_DICT | ml;
+}
+// Tries the two slots of the position's bucket (later slot wins ties, as in SearchInStaticDictionary); returns the packed
+// candidate or 0.  max_len = bytes left in the range, max_backward_here = min(absolute position, window - 16).
+BRO_HD uint32_t dict_candidate(const DictView& D, int hash_type, const uint8_t* cur, uint32_t max_len, uint32_t max_backward_here) {
+  uint32_t best = 0, best_score = BRO_MIN_SCORE;
   const uint32_t key = dict_hash14(load32(cur)) << 1;
   for (uint32_t s = 0; s < 2; ++s) {
     const uint32_t item = D.hash[key + s];
@@ -61,33 +69,23 @@ BRO_HD bool dict_search(const DictView& D, int hash_type, const uint8_t* cur, ui
     const uint8_t* w = D.words + dict_offset(len) + len * idx;
     uint32_t ml = 0;
     while (ml < len && cur[ml] == w[ml]) ++ml;
-    if (ml + 10u <= len || ml < 4) continue;  // ml < 4: the slot was reached through a hash collision (the reference would accept
-                                              // such a 1..3 byte OmitLast match when the window is tiny; not worth a byte-wise path)
-    const uint32_t backward = max_backward_here + 1u + idx + (dict_omit_last_transform(len - ml) << dict_size_bits(len));
-    if (backward > 0x3FFFFFCu) continue;
-    const uint32_t score = score_regular(hash_type, ml, backward);
-    if (score < m->score) continue;
-    m->len = pack_dict_len(ml, len);
-    m->dist = backward;
-    m->score = score;
-    found = true;
+    if (ml + 10u <= len || ml < 4) continue;  // ml < 4: the slot was reached through a hash collision
+    const uint32_t word_id = idx + (dict_omit_last_transform(len - ml) << dict_size_bits(len));
+    const uint32_t score = score_regular(hash_type, ml, max_backward_here + 1u + word_id);
+    if (score < best_score) continue;
+    best = best_pack_dict(ml, len, idx);
+    best_score = score;
   }
-  return found;
+  return best;
 }
-
-// sample k of the per-unit gate: does position ustart + 64 k start a usable dictionary word ?
-BRO_HD bool dict_gate_sample(const DictView& D, int hash_type, const uint8_t* data, uint32_t ustart, uint32_t uend, uint32_t k) {
-  const uint32_t p = ustart + 64u * k;
-  if (p + 8u > uend) return false;
-  Match m;
-  m.len = m.dist = 0;
-  m.score = BRO_MIN_SCORE;
-  return dict_search(D, hash_type, data + p, uend - p, 0x3FFFF0u, &m);
-}
-BRO_HD bool dict_unit_gate(const DictView& D, int hash_type, const uint8_t* data, uint32_t ustart, uint32_t uend) {
-  for (uint32_t k = 0; k < 64; ++k)
-    if (dict_gate_sample(D, hash_type, data, ustart, uend, k)) return true;
-  return false;
+// Parse side: decodes a dictionary candidate of best[] for a position with max_len bytes left in its unit.
+BRO_HD bool dict_decode(uint32_t b, int hash_type, uint32_t max_len, uint32_t max_backward_here, Match* m) {
+  const uint32_t ml = b & 0x7Fu, wl = ml + ((b >> 26) & 0xFu);
+  if (wl > max_len) return false;
+  m->len = pack_dict_len(ml, wl);
+  m->dist = max_backward_here + 1u + ((b >> 8) & 0x3FFFFu);
+  m->score = score_regular(hash_type, ml, m->dist);
+  return true;
 }
 
 }  // namespace bro

@@ -378,6 +378,8 @@ struct B200Encoder {
       ma.depth = P.depth;
       ma.lcap = P.lcap;
       ma.max_backward = P.max_backward;
+      ma.dict = W.dict;
+      ma.use_dict = P.use_dict;
       const size_t smem = (size_t)(MATCH_THREADS + P.depth) * 6 * 4;
       mark(L, B200_ST_MATCH);
       if (P.depth >= 64) k_match<true><<<(count + MATCH_THREADS - 1) / MATCH_THREADS, MATCH_THREADS, smem, stream>>>(ma);

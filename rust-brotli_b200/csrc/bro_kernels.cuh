@@ -333,7 +333,42 @@ struct MatchArgs {
   uint32_t* best;
   int hash_type, key_bits, depth;
   uint32_t lcap, max_backward;
+  DictView dict;            // static dictionary (device copies)
+  int use_dict;
 };
+
+// dict_candidate() of bro_dict.cuh with the position's first 16 bytes already in registers and 8-byte word compares
+__device__ __forceinline__ uint32_t dict_candidate_dev(const DictView& D, int hash_type, uint32_t m0, uint32_t m1, uint32_t m2,
+                                                       uint32_t m3, const uint8_t* cur, uint32_t max_len, uint32_t mb) {
+  uint32_t best = 0, best_score = BRO_MIN_SCORE;
+  const uint32_t key = dict_hash14(m0) << 1;
+#pragma unroll
+  for (uint32_t s = 0; s < 2; ++s) {
+    const uint32_t item = D.hash[key + s];
+    const uint32_t wl = item & 31u, idx = item >> 5;
+    if (item == 0 || wl > max_len) continue;
+    const uint8_t* w = D.words + dict_offset(wl) + wl * idx;
+    uint64_t x = ldu64(w) ^ (((uint64_t)m1 << 32) | m0);
+    if ((uint32_t)x != 0) continue;  // hash collision
+    uint32_t ml = x ? ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : 8u;
+    if (ml == 8u && wl > 8u) {
+      x = ldu64(w + 8) ^ (((uint64_t)m3 << 32) | m2);
+      ml += x ? ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : 8u;
+      if (ml == 16u && wl > 16u) {
+        x = ldu64(w + 16) ^ ldu64(cur + 16);
+        ml += x ? ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : 8u;
+      }
+    }
+    ml = bmin(ml, wl);
+    if (ml + 10u <= wl) continue;
+    const uint32_t word_id = idx + (dict_omit_last_transform(wl - ml) << dict_size_bits(wl));
+    const uint32_t score = score_regular(hash_type, ml, mb + 1u + word_id);
+    if (score < best_score) continue;
+    best = best_pack_dict(ml, wl, idx);
+    best_score = score;
+  }
+  return best;
+}
 
 __device__ __forceinline__ void load16_unaligned(const uint8_t* p, uint32_t* w) {
   const uint32_t* q = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
@@ -434,7 +469,10 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
       }
     }
   }
-  a.best[p] = best_len ? ((best_dist << 8) | best_len) : 0u;
+  uint32_t outv = best_len ? ((best_dist << 8) | best_len) : 0u;
+  if (best_len == 0 && a.use_dict && a.n - p >= 8)  // nothing in the bucket: static dictionary (mod.rs:1797, :1942)
+    outv = dict_candidate_dev(a.dict, a.hash_type, s_d0[i], s_d1[i], s_d2[i], s_d3[i], a.data + p, a.n - p, bmin(p, a.max_backward));
+  a.best[p] = outv;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -471,7 +509,7 @@ __device__ __forceinline__ uint32_t warp_lcp_ext(const uint8_t* cur, uint32_t ba
 template <int NL>
 __device__ __forceinline__ uint32_t parse_unit_warp(const EncParams& P, const uint8_t* data, const uint32_t* best,
                                                     uint32_t ustart, uint32_t uend, RawCmd* out, uint32_t* tail,
-                                                    uint32_t* ncopy, const DictView* D, int32_t* dc) {
+                                                    uint32_t* ncopy, bool D, int32_t* dc) {
   constexpr int G = 32 / NL;
   constexpr uint32_t CAPA = 8;  // bytes compared per probe in the parallel phase
   const uint32_t FULL = 0xffffffffu;
@@ -532,6 +570,11 @@ __device__ __forceinline__ uint32_t parse_unit_warp(const EncParams& P, const ui
       }
       const uint32_t b = __shfl_sync(FULL, mybest, j);
       const uint32_t blen = b & 0xFFu;
+      if (b & BRO_BEST_DICT) {  // dictionary candidate of the match stage: only when nothing else matched
+        o->len = best_len; o->dist = best_dist; o->score = best_score;
+        if (!found && D) found = dict_decode(b, P.hash_type, max_len, max_backward_at(p), o);
+        return found;
+      }
       if (blen != 0) {
         const uint32_t bdist = b >> 8;
         uint32_t len = bmin(blen, max_len);
@@ -542,7 +585,6 @@ __device__ __forceinline__ uint32_t parse_unit_warp(const EncParams& P, const ui
         }
       }
       o->len = best_len; o->dist = best_dist; o->score = best_score;
-      if (!found && D) found = dict_search(*D, P.hash_type, data + p, max_len, max_backward_at(p), o);  // warp-uniform
       return found;
     };
 
@@ -621,7 +663,7 @@ __device__ __forceinline__ uint32_t lane_lcp_ext(const uint8_t* cur, uint32_t ba
 // walk only reads finished (found, len, dist, score) tuples: ballots locate the next match, shuffles fetch it.
 __device__ __forceinline__ uint32_t parse_unit_warp4(const EncParams& P, const uint8_t* data, const uint32_t* best,
                                                      uint32_t ustart, uint32_t uend, RawCmd* out, uint32_t* tail,
-                                                     uint32_t* ncopy, const DictView* D, int32_t* dc) {
+                                                     uint32_t* ncopy, bool D, int32_t* dc) {
   constexpr int G = 8;
   constexpr uint32_t CAPA = 8;
   const uint32_t FULL = 0xffffffffu;
@@ -674,7 +716,11 @@ __device__ __forceinline__ uint32_t parse_unit_warp4(const EncParams& P, const u
     if (p_ok && i_lane == 0) {  // bucket candidate from the match kernel must be strictly better
       const uint32_t b = best[p];
       const uint32_t blen = b & 0xFFu;
-      if (blen != 0) {
+      if (b & BRO_BEST_DICT) {  // dictionary candidate of the match stage: only when the cache gave nothing
+        Match dm;
+        const uint32_t mb = near_start ? bmin(p + P.abs_base, P.max_backward) : P.max_backward;
+        if (!f_found && D && dict_decode(b, 5, maxl, mb, &dm)) { f_found = true; f_len = dm.len; f_dist = dm.dist; f_score = dm.score; }
+      } else if (blen != 0) {
         const uint32_t bdist = b >> 8;
         uint32_t len = bmin(blen, maxl);
         if (blen >= P.lcap && maxl > len) len = lane_lcp_ext(data + p, bdist, len, maxl);
@@ -683,43 +729,6 @@ __device__ __forceinline__ uint32_t parse_unit_warp4(const EncParams& P, const u
           if (f_score < score) { f_score = score; f_len = len; f_dist = bdist; f_found = true; }
         }
       }
-    }
-    if (D) {  // unit gate open (warp-uniform): lanes 4j+1 / 4j+2 probe the two table slots of position j (dict_search of
-              // bro_dict.cuh, one slot per lane, 8-byte compares); lane 4j takes the result if nothing else matched
-      uint32_t d_len = 0, d_dist = 0, d_score = 0;
-      if (p_ok && (i_lane == 1 || i_lane == 2)) {
-        const uint64_t cw = ldu64(data + p);
-        const uint32_t item = D->hash[(dict_hash14((uint32_t)cw) << 1) + (i_lane - 1u)];
-        const uint32_t wl = item & 31u, idx = item >> 5;
-        if (item != 0 && wl <= maxl) {
-          const uint8_t* w = D->words + dict_offset(wl) + wl * idx;
-          uint32_t ml = 0;
-          uint64_t x = cw ^ ldu64(w);
-          if ((uint32_t)x == 0) {  // the 4 hashed bytes agree (anything else is a hash collision)
-            ml = x ? ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : 8u;
-            while (ml == 8u || ml == 16u) {
-              if (ml >= wl) break;
-              x = ldu64(data + p + ml) ^ ldu64(w + ml);
-              ml += x ? ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : 8u;
-              if (x) break;
-            }
-            ml = bmin(ml, wl);
-          }
-          if (ml >= 4u && ml + 10u > wl) {
-            const uint32_t mb = near_start ? bmin(p + P.abs_base, P.max_backward) : P.max_backward;
-            const uint32_t backward = mb + 1u + idx + (dict_omit_last_transform(wl - ml) << dict_size_bits(wl));
-            const uint32_t score = score_regular(5, ml, backward);
-            if (backward <= 0x3FFFFFCu && score >= BRO_MIN_SCORE) { d_len = pack_dict_len(ml, wl); d_dist = backward; d_score = score; }
-          }
-        }
-      }
-      const int s1 = (int)((lane & ~3u) + 1u), s2 = s1 + 1;
-      const uint32_t l1 = __shfl_sync(FULL, d_len, s1), l2 = __shfl_sync(FULL, d_len, s2);
-      const uint32_t sc1 = __shfl_sync(FULL, d_score, s1), sc2 = __shfl_sync(FULL, d_score, s2);
-      const bool take2 = l2 != 0 && (l1 == 0 || sc2 >= sc1);  // the later slot wins ties, as in the sequential search
-      const uint32_t dd = __shfl_sync(FULL, d_dist, take2 ? s2 : s1);
-      const uint32_t dl = take2 ? l2 : l1, ds = take2 ? sc2 : sc1;
-      if (i_lane == 0 && !f_found && dl != 0) { f_found = true; f_len = dl; f_dist = dd; f_score = ds; }
     }
     // lane 4*j now holds the finished result of position wbase + j
     uint32_t found8 = __ballot_sync(FULL, f_found && i_lane == 0);  // bits 0,4,8,.. -> compress to bits 0..7
@@ -805,14 +814,7 @@ __global__ void __launch_bounds__(PARSE_WARPS * 32) k_parse(Workspace W) {
   const uint32_t s = u * P.unit, e = bmin(P.n, s + P.unit);
   uint32_t tail, ncopy, ncmd;
   const uint32_t cu = P.unit / 2 + 1;
-  // dictionary gate of the unit (dict_unit_gate of bro_dict.cuh, two samples per lane)
-  bool gate = false;
-  if (P.use_dict) {
-    const uint32_t lane = threadIdx.x & 31;
-    gate = __any_sync(0xffffffffu, dict_gate_sample(W.dict, P.hash_type, W.data, s, e, lane) ||
-                                       dict_gate_sample(W.dict, P.hash_type, W.data, s, e, lane + 32));
-  }
-  const DictView* D = gate ? &W.dict : nullptr;
+  const bool D = P.use_dict != 0;
   // phase 0: warm-up over the BRO_WARMUP_BYTES in front of the unit (commands discarded, only the distance cache is kept);
   // phase 1: the unit itself.  One loop body so that the parse code is instantiated once.
   int32_t dc[4] = {0x3fffffff, 0x3fffffff, 0x3fffffff, 0x3fffffff};
@@ -822,7 +824,7 @@ __global__ void __launch_bounds__(PARSE_WARPS * 32) k_parse(Workspace W) {
   for (int phase = warm ? 0 : 1; phase < 2; ++phase) {
     const uint32_t rs = phase ? s : s - BRO_WARMUP_BYTES, re = phase ? e : s;
     RawCmd* const o = phase ? out : nullptr;
-    const DictView* const Dp = phase ? D : nullptr;
+    const bool Dp = D;
     if (P.n_last == 4 && P.hash_type != 9) ncmd = parse_unit_warp4(P, W.data, W.best, rs, re, o, &tail, &ncopy, Dp, dc);
     else if (P.n_last <= 4) ncmd = parse_unit_warp<4>(P, W.data, W.best, rs, re, o, &tail, &ncopy, Dp, dc);
     else ncmd = parse_unit_warp<16>(P, W.data, W.best, rs, re, o, &tail, &ncopy, Dp, dc);

@@ -94,10 +94,10 @@ BRO_HD int32_t cache_candidate(const int32_t* dc, int i) {
 }
 
 // Best match at pos: last-distance probes (serial state) combined with the precomputed bucket candidate.
-// D != nullptr: the unit's dictionary gate is open; a dictionary match is looked for when nothing else was found and comes
-// back with Match::len packed by pack_dict_len().
+// use_dict: a dictionary candidate left in best[] by the match stage is taken when nothing else was found; it comes back
+// with Match::len packed by pack_dict_len().
 BRO_HD_NOINLINE bool find_match(const EncParams& P, const uint8_t* data, const uint32_t* best, const int32_t* dc,
-                                uint32_t pos, uint32_t max_len, Match* out, const DictView* D) {
+                                uint32_t pos, uint32_t max_len, Match* out, bool use_dict) {
   const uint32_t max_backward = (P.abs_base >= P.max_backward) ? P.max_backward : bmin(pos + P.abs_base, P.max_backward);
   uint32_t best_score = BRO_MIN_SCORE, best_len = 0, best_dist = 0;
   bool found = false;
@@ -117,6 +117,11 @@ BRO_HD_NOINLINE bool find_match(const EncParams& P, const uint8_t* data, const u
     }
   }
   uint32_t b = best[pos];
+  if (b & BRO_BEST_DICT) {  // dictionary candidate: only when nothing else matched
+    out->len = best_len; out->dist = best_dist; out->score = best_score;
+    if (!found && use_dict) found = dict_decode(b, P.hash_type, max_len, max_backward, out);
+    return found;
+  }
   uint32_t blen = b & 0xFFu;
   if (blen != 0) {
     uint32_t bdist = b >> 8;
@@ -131,7 +136,6 @@ BRO_HD_NOINLINE bool find_match(const EncParams& P, const uint8_t* data, const u
     }
   }
   out->len = best_len; out->dist = best_dist; out->score = best_score;
-  if (!found && D) found = dict_search(*D, P.hash_type, cur, max_len, max_backward, out);
   return found;
 }
 
@@ -139,7 +143,7 @@ BRO_HD_NOINLINE bool find_match(const EncParams& P, const uint8_t* data, const u
 // (copy_len >= 2) to out[] unless out is null, returns their number; *tail = literals after the last copy, *ncopy = total
 // bytes covered by copies.
 BRO_HD_NOINLINE uint32_t parse_range(const EncParams& P, const uint8_t* data, const uint32_t* best, uint32_t rstart,
-                                     uint32_t rend, RawCmd* out, uint32_t* tail, uint32_t* ncopy, const DictView* D, int32_t* dc) {
+                                     uint32_t rend, RawCmd* out, uint32_t* tail, uint32_t* ncopy, bool D, int32_t* dc) {
   const uint32_t hash_type_len = P.hash_type == 6 ? 8u : 4u;
   const uint32_t window = P.quality < 9 ? 64u : 512u;
   const uint32_t uend = rend;
@@ -204,19 +208,17 @@ BRO_HD_NOINLINE uint32_t parse_range(const EncParams& P, const uint8_t* data, co
 // warm-up are discarded).  Without it every unit starts with an unknown cache and repetitive, record-structured input
 // loses ~1.4 % (4 MB of JSON logs, q5); with it +0.06 %.  The cache is only a heuristic input of the match choice: the
 // real short codes are assigned by the finalise stage from the true distance sequence.
-#define BRO_WARMUP_BYTES 512u
+#define BRO_WARMUP_BYTES 256u
 
-// One parse unit [ustart, uend): warm-up (not for the first unit of a metablock, whose cache really is unknown),
-// dictionary gate, parse.
+// One parse unit [ustart, uend): warm-up (not for the first unit of a metablock, whose cache really is unknown), parse.
 BRO_HD_NOINLINE uint32_t parse_unit(const EncParams& P, const uint8_t* data, const uint32_t* best, uint32_t ustart,
-                                    uint32_t uend, RawCmd* out, uint32_t* tail, uint32_t* ncopy, const DictView* dict) {
+                                    uint32_t uend, RawCmd* out, uint32_t* tail, uint32_t* ncopy) {
   int32_t dc[4] = {0x3fffffff, 0x3fffffff, 0x3fffffff, 0x3fffffff};
   if ((ustart / P.unit) % P.mb_units != 0 && ustart >= BRO_WARMUP_BYTES) {
     uint32_t t2, c2;
-    parse_range(P, data, best, ustart - BRO_WARMUP_BYTES, ustart, nullptr, &t2, &c2, nullptr, dc);
+    parse_range(P, data, best, ustart - BRO_WARMUP_BYTES, ustart, nullptr, &t2, &c2, P.use_dict != 0, dc);
   }
-  const DictView* D = (dict && P.use_dict && dict_unit_gate(*dict, P.hash_type, data, ustart, uend)) ? dict : nullptr;
-  return parse_range(P, data, best, ustart, uend, out, tail, ncopy, D, dc);
+  return parse_range(P, data, best, ustart, uend, out, tail, ncopy, P.use_dict != 0, dc);
 }
 
 }  // namespace bro
