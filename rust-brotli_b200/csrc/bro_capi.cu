@@ -21,6 +21,7 @@ struct EncoderParams {  // the subset of BrotliEncoderParams (backward_reference
   int mode = 0;
   uint64_t size_hint = 0;
   int disable_ctx = 0;
+  int no_dictionary = 0;
   int catable = 0, appendable = 0, magic_number = 0, byte_align = 0, bare_stream = 0;
 };
 
@@ -32,6 +33,7 @@ bool apply_param(EncoderParams& p, int key, uint32_t value) {
     case BROTLI_PARAM_LGBLOCK: return true;  // parse granularity is a device-side constant here
     case BROTLI_PARAM_DISABLE_LITERAL_CONTEXT_MODELING: p.disable_ctx = (int)value; return true;
     case BROTLI_PARAM_SIZE_HINT: p.size_hint = value; return true;
+    case BROTLI_PARAM_NO_DICTIONARY: p.no_dictionary = value != 0; return true;
     case BROTLI_PARAM_LARGE_WINDOW: return true;  // windows above 2^24 are clamped (SanitizeParams encode.rs:546-558)
     case BROTLI_PARAM_CATABLE: p.catable = value != 0; if (p.catable) p.appendable = 1; return true;
     case BROTLI_PARAM_APPENDABLE: p.appendable = value != 0; return true;
@@ -138,6 +140,7 @@ static bool state_emit(BrotliEncoderStateStruct* s, bool last) {
   size_t old = s->output.size();
   s->output.resize(old + cap);
   b200_encoder_set_option(s->enc, B200_OPT_CTX_MODEL, s->params.disable_ctx ? 0 : 1);
+  b200_encoder_set_option(s->enc, B200_OPT_DICT, s->params.no_dictionary ? 0 : 1);
   uint64_t hint = s->params.size_hint ? s->params.size_hint : s->input.size();
   int ok = b200_encoder_compress_range(s->enc, s->params.quality, s->params.lgwin, hint, s->input.data(), s->input.size(), start, len,
                                        first ? 1 : 0, last ? 1 : 0, last ? 0 : 1, s->output.data() + old, cap, &got, 0);
@@ -205,6 +208,7 @@ BROTLI_BOOL BrotliEncoderCompress(int quality, int lgwin, BrotliEncoderMode mode
   {
     std::lock_guard<std::mutex> lk(*mu);
     b200_encoder_set_option(enc, B200_OPT_CTX_MODEL, 1);
+    b200_encoder_set_option(enc, B200_OPT_DICT, 1);
     ok = b200_encoder_compress(enc, quality, lgwin, input, input_size, encoded, out_cap, &got, 0);
   }
   if (!ok) {  // no CPU-produced stream, ever: a device failure (or a too-small output buffer) is reported as failure
@@ -243,6 +247,7 @@ static int32_t compress_multi_impl(const std::vector<B200Encoder*>& encs, std::v
       // compress_part threading/mod.rs:337-383: size_hint = shard length
       uint64_t hint = p.size_hint ? p.size_hint : (b - a);
       b200_encoder_set_option(encs[g], B200_OPT_CTX_MODEL, p.disable_ctx ? 0 : 1);
+      b200_encoder_set_option(encs[g], B200_OPT_DICT, p.no_dictionary ? 0 : 1);
       oks[i] = b200_encoder_compress_range(encs[g], p.quality, p.lgwin, hint, input, input_size, a, b - a, i == 0 ? 1 : 0,
                                            i + 1 == shards ? 1 : 0, i + 1 == shards ? 0 : 1, outs[i].data(), cap, &got, 0);
       outs[i].resize(oks[i] ? got : 0);
