@@ -382,8 +382,15 @@ struct B200Encoder {
       ma.use_dict = P.use_dict;
       const size_t smem = (size_t)(MATCH_THREADS + P.depth) * 6 * 4;
       mark(L, B200_ST_MATCH);
-      if (P.depth >= 64) k_match<true><<<(count + MATCH_THREADS - 1) / MATCH_THREADS, MATCH_THREADS, smem, stream>>>(ma);
-      else k_match<false><<<(count + MATCH_THREADS - 1) / MATCH_THREADS, MATCH_THREADS, smem, stream>>>(ma);
+      const uint32_t mgrid = (count + MATCH_THREADS - 1) / MATCH_THREADS;
+      switch (P.depth) {  // bucket depth = 1 << block_bits: 16 (q5) .. 256 (q9, and lgwin <= 16)
+        case 16: k_match<false, 16><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
+        case 32: k_match<false, 32><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
+        case 64: k_match<true, 64><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
+        case 128: k_match<true, 128><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
+        case 256: k_match<true, 256><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
+        default: fprintf(stderr, "[brotli_b200] unsupported bucket depth %d\n", P.depth); return false;
+      }
       launches += 1;
     }
     mark(L, B200_ST_PARSE);

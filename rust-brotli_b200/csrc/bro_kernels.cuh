@@ -384,17 +384,18 @@ __device__ __forceinline__ void load16_unaligned(const uint8_t* p, uint32_t* w) 
 // PREFILTER (deep buckets, q7..q9): a farther candidate only wins if it is strictly longer, so it is rejected on the byte at
 // index best_len before the full comparison (the reference's cur[best_len] != prev[best_len] test, mod.rs:1765-1773);
 // same result, and for the shallow q5/q6 buckets the extra branch costs more than it saves.
-template <bool PREFILTER>
+// DEPTH = bucket depth (compile time: every shared-memory array offset becomes an immediate).
+template <bool PREFILTER, int DEPTH>
 __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
   extern __shared__ uint32_t smem[];
-  const uint32_t E = MATCH_THREADS + (uint32_t)a.depth;
+  constexpr uint32_t E = MATCH_THREADS + (uint32_t)DEPTH;
   uint32_t* s_pos = smem;
   uint32_t* s_key = smem + E;
   uint32_t* s_d0 = smem + 2 * E;
   uint32_t* s_d1 = smem + 3 * E;
   uint32_t* s_d2 = smem + 4 * E;
   uint32_t* s_d3 = smem + 5 * E;
-  const int64_t j0 = (int64_t)blockIdx.x * MATCH_THREADS - a.depth;  // sorted index of smem entry 0
+  const int64_t j0 = (int64_t)blockIdx.x * MATCH_THREADS - DEPTH;  // sorted index of smem entry 0
   for (uint32_t i = threadIdx.x; i < E; i += MATCH_THREADS) {
     int64_t j = j0 + i;
     uint32_t pos = 0xFFFFFFFFu, key = 0xFFFFFFFFu, w[4] = {0, 0, 0, 0};
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
     s_pos[i] = pos; s_key[i] = key; s_d0[i] = w[0]; s_d1[i] = w[1]; s_d2[i] = w[2]; s_d3[i] = w[3];
   }
   __syncthreads();
-  const uint32_t i = threadIdx.x + (uint32_t)a.depth;
+  const uint32_t i = threadIdx.x + (uint32_t)DEPTH;
   const uint32_t prel = s_pos[i];
   if (prel == 0xFFFFFFFFu || prel < a.payload_begin) return;
   const uint32_t p = a.origin + prel;
@@ -417,13 +418,24 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
     const uint32_t max_backward = bmin(p, a.max_backward);
     const uint32_t m0 = s_d0[i], m1 = s_d1[i], m2 = s_d2[i], m3 = s_d3[i];
     bool done = false;
-    for (uint32_t cbase = 0; cbase < (uint32_t)a.depth && !done; cbase += 16) {
+    for (uint32_t cbase = 0; cbase < (uint32_t)DEPTH && !done; cbase += 16) {
       // phase 1 (branch-free, unrolled): which of the next 16 older entries share the bucket key and the first 4 bytes
       uint32_t mask = 0;
+      if (PREFILTER && best_len >= 4 && best_len < 16) {
+        // deep buckets: once a match is known, a farther candidate must also agree on the byte at index best_len
+        const uint32_t wsel = (2u + (best_len >> 2)) * E, sh = (best_len & 3u) * 8u;
+        const uint32_t mw = smem[wsel + i];
 #pragma unroll
-      for (uint32_t c = 0; c < 16; ++c) {
-        const uint32_t ci = i - 1u - cbase - c;
-        mask |= (uint32_t)((s_key[ci] == key) & (s_d0[ci] == m0)) << c;
+        for (uint32_t c = 0; c < 16; ++c) {
+          const uint32_t ci = i - 1u - cbase - c;
+          mask |= (uint32_t)((s_key[ci] == key) & (s_d0[ci] == m0) & ((((smem[wsel + ci] ^ mw) >> sh) & 0xFFu) == 0u)) << c;
+        }
+      } else {
+#pragma unroll
+        for (uint32_t c = 0; c < 16; ++c) {
+          const uint32_t ci = i - 1u - cbase - c;
+          mask |= (uint32_t)((s_key[ci] == key) & (s_d0[ci] == m0)) << c;
+        }
       }
       if (s_key[i - 16u - cbase] != key) done = true;  // the bucket ends inside this group: nothing older can match
       // phase 2: full evaluation of the survivors, nearest first
@@ -661,10 +673,19 @@ __device__ __forceinline__ uint32_t lane_lcp_ext(const uint8_t* cur, uint32_t ba
 // candidate fold of find_match() is exactly "highest score, ties to the lower cache index", so all 8 positions of a
 // window are resolved completely in parallel (4 lanes per position, 2 shuffle-max steps) and the serial greedy / lazy
 // walk only reads finished (found, len, dist, score) tuples: ballots locate the next match, shuffles fetch it.
+//
+// NL = 10 / 16 (q7..q9, incl. the H9 scores): same layout, each of the 4 lanes of a position probes candidates
+// i = lane, lane + 4, ...  The sequential fold with its "must be longer" pre-filter (find_match) reduces to: the longest
+// valid candidate wins, lowest index first; only among candidates that reach max_len does the score (i.e. the per-index
+// bonus) decide -- 135 points per byte always outweigh the bonus spread (<= 47).  That is a max over the key
+// len << 12 | (len == max_len ? bonus : 0) << 4 | (15 - i).
+template <int NL>
 __device__ __forceinline__ uint32_t parse_unit_warp4(const EncParams& P, const uint8_t* data, const uint32_t* best,
                                                      uint32_t ustart, uint32_t uend, RawCmd* out, uint32_t* tail,
                                                      uint32_t* ncopy, bool D, int32_t* dc) {
   constexpr int G = 8;
+  constexpr int K = (NL + 3) / 4;  // candidates per lane
+  const int ht = NL == 4 ? 5 : P.hash_type;  // score family (5 and 6 share one)
   constexpr uint32_t CAPA = 8;
   const uint32_t FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x & 31;
@@ -672,7 +693,7 @@ __device__ __forceinline__ uint32_t parse_unit_warp4(const EncParams& P, const u
   const bool il1 = (lane & 1u) != 0, il2 = (lane & 2u) != 0;
   int32_t dc0 = dc[0], dc1 = dc[1], dc2 = dc[2], dc3 = dc[3];
   const uint32_t htl = P.hash_type == 6 ? 8u : 4u;
-  const uint32_t window = 64u;  // quality < 9 on this path
+  const uint32_t window = (NL == 4 || P.quality < 9) ? 64u : 512u;
   uint32_t pos = ustart, insert_len = 0, ncmd = 0, copied = 0;
   uint32_t arh = pos + window;
   bool have_m = false;
@@ -687,29 +708,62 @@ __device__ __forceinline__ uint32_t parse_unit_warp4(const EncParams& P, const u
     const bool p_ok = p < uend;
     const uint32_t maxl = p_ok ? uend - p : 0u;
     uint32_t clen = 0, cdist = 0, key = 0;
-    if (p_ok) {
-      const int32_t back = il2 ? (il1 ? dc3 : dc2) : (il1 ? dc1 : dc0);  // selects, not branches
-      const uint32_t mb = near_start ? bmin(p + P.abs_base, P.max_backward) : P.max_backward;
-      if (back > 0 && (uint32_t)back <= mb) {
-        const uint64_t x = ldu64(data + p) ^ ldu64(data + p - back);
-        uint32_t len = x ? ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : CAPA;
-        len = bmin(len, maxl);
-        if (len == CAPA && maxl > CAPA) len = lane_lcp_ext(data + p, (uint32_t)back, CAPA, maxl);
-        if (len >= 3 || (len == 2 && i_lane < 2)) {
-          const uint32_t score = score_last_distance(5, len, i_lane);
-          key = (score << 2) | (3u - i_lane);
-          clen = len;
-          cdist = (uint32_t)back;
+    if constexpr (NL == 4) {
+      if (p_ok) {
+        const int32_t back = il2 ? (il1 ? dc3 : dc2) : (il1 ? dc1 : dc0);  // selects, not branches
+        const uint32_t mb = near_start ? bmin(p + P.abs_base, P.max_backward) : P.max_backward;
+        if (back > 0 && (uint32_t)back <= mb) {
+          const uint64_t x = ldu64(data + p) ^ ldu64(data + p - back);
+          uint32_t len = x ? ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : CAPA;
+          len = bmin(len, maxl);
+          if (len == CAPA && maxl > CAPA) len = lane_lcp_ext(data + p, (uint32_t)back, CAPA, maxl);
+          if (len >= 3 || (len == 2 && i_lane < 2)) {
+            const uint32_t score = score_last_distance(5, len, i_lane);
+            key = (score << 2) | (3u - i_lane);
+            clen = len;
+            cdist = (uint32_t)back;
+          }
         }
       }
-    }
-    {  // best of the 4 cache candidates of this position
-      uint32_t k = key;
-      k = max(k, __shfl_xor_sync(FULL, k, 1));
-      k = max(k, __shfl_xor_sync(FULL, k, 2));
-      const int src = (int)((lane & ~3u) + (3u - (k & 3u)));
-      const uint32_t wl = __shfl_sync(FULL, clen, src), wd = __shfl_sync(FULL, cdist, src);
-      key = k; clen = wl; cdist = wd;
+      {  // best of the 4 cache candidates of this position
+        uint32_t k = key;
+        k = max(k, __shfl_xor_sync(FULL, k, 1));
+        k = max(k, __shfl_xor_sync(FULL, k, 2));
+        const int src = (int)((lane & ~3u) + (3u - (k & 3u)));
+        const uint32_t wl = __shfl_sync(FULL, clen, src), wd = __shfl_sync(FULL, cdist, src);
+        key = k; clen = wl; cdist = wd;
+      }
+    } else {
+      const int32_t dca[4] = {dc0, dc1, dc2, dc3};
+      if (p_ok) {
+        const uint32_t mb = near_start ? bmin(p + P.abs_base, P.max_backward) : P.max_backward;
+        const uint64_t cw = ldu64(data + p);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int i = (int)i_lane + 4 * k;
+          if (i < NL) {
+            const int32_t back = cache_candidate(dca, i);
+            if (back > 0 && (uint32_t)back <= mb) {
+              const uint64_t x = cw ^ ldu64(data + p - back);
+              uint32_t len = x ? ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : CAPA;
+              len = bmin(len, maxl);
+              if (len == CAPA && maxl > CAPA) len = lane_lcp_ext(data + p, (uint32_t)back, CAPA, maxl);
+              if (len >= 3 || (len == 2 && i < 2)) {
+                const uint32_t bonus = len == maxl ? score_last_distance(ht, 0, (uint32_t)i) - 1880u : 0u;
+                key = max(key, ((len << 12) | (bonus << 4) | (uint32_t)(15 - i)) + 1u);
+              }
+            }
+          }
+        }
+      }
+      key = max(key, __shfl_xor_sync(FULL, key, 1));
+      key = max(key, __shfl_xor_sync(FULL, key, 2));
+      if (key) {  // every lane of the position decodes the winner; key keeps "found", the score moves to the usual place
+        const uint32_t wi = 15u - ((key - 1u) & 15u);
+        clen = (key - 1u) >> 12;
+        cdist = (uint32_t)cache_candidate(dca, (int)wi);
+        key = score_last_distance(ht, clen, wi) << 2;
+      }
     }
     uint32_t f_score = key ? (key >> 2) : BRO_MIN_SCORE, f_len = key ? clen : 0u, f_dist = key ? cdist : 0u;
     bool f_found = key != 0;
@@ -719,13 +773,13 @@ __device__ __forceinline__ uint32_t parse_unit_warp4(const EncParams& P, const u
       if (b & BRO_BEST_DICT) {  // dictionary candidate of the match stage: only when the cache gave nothing
         Match dm;
         const uint32_t mb = near_start ? bmin(p + P.abs_base, P.max_backward) : P.max_backward;
-        if (!f_found && D && dict_decode(b, 5, maxl, mb, &dm)) { f_found = true; f_len = dm.len; f_dist = dm.dist; f_score = dm.score; }
+        if (!f_found && D && dict_decode(b, ht, maxl, mb, &dm)) { f_found = true; f_len = dm.len; f_dist = dm.dist; f_score = dm.score; }
       } else if (blen != 0) {
         const uint32_t bdist = b >> 8;
         uint32_t len = bmin(blen, maxl);
         if (blen >= P.lcap && maxl > len) len = lane_lcp_ext(data + p, bdist, len, maxl);
         if (len >= 4) {
-          const uint32_t score = score_regular(5, len, bdist);
+          const uint32_t score = score_regular(ht, len, bdist);
           if (f_score < score) { f_score = score; f_len = len; f_dist = bdist; f_found = true; }
         }
       }
@@ -825,9 +879,10 @@ __global__ void __launch_bounds__(PARSE_WARPS * 32) k_parse(Workspace W) {
     const uint32_t rs = phase ? s : s - BRO_WARMUP_BYTES, re = phase ? e : s;
     RawCmd* const o = phase ? out : nullptr;
     const bool Dp = D;
-    if (P.n_last == 4 && P.hash_type != 9) ncmd = parse_unit_warp4(P, W.data, W.best, rs, re, o, &tail, &ncopy, Dp, dc);
-    else if (P.n_last <= 4) ncmd = parse_unit_warp<4>(P, W.data, W.best, rs, re, o, &tail, &ncopy, Dp, dc);
-    else ncmd = parse_unit_warp<16>(P, W.data, W.best, rs, re, o, &tail, &ncopy, Dp, dc);
+    if (P.n_last == 4 && P.hash_type != 9) ncmd = parse_unit_warp4<4>(P, W.data, W.best, rs, re, o, &tail, &ncopy, Dp, dc);
+    else if (P.n_last == 10) ncmd = parse_unit_warp4<10>(P, W.data, W.best, rs, re, o, &tail, &ncopy, Dp, dc);
+    else if (P.n_last == 16) ncmd = parse_unit_warp4<16>(P, W.data, W.best, rs, re, o, &tail, &ncopy, Dp, dc);
+    else ncmd = parse_unit_warp<16>(P, W.data, W.best, rs, re, o, &tail, &ncopy, Dp, dc);  // generic reference implementation
   }
   if ((threadIdx.x & 31) == 0) {
     W.unit_ncmd[u] = ncmd;
