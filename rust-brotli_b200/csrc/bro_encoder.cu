@@ -386,9 +386,9 @@ struct B200Encoder {
       switch (P.depth) {  // bucket depth = 1 << block_bits: 16 (q5) .. 256 (q9, and lgwin <= 16)
         case 16: k_match<false, 16><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
         case 32: k_match<false, 32><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
-        case 64: k_match<true, 64><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
-        case 128: k_match<true, 128><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
-        case 256: k_match<true, 256><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
+        case 64: k_match_deep<64><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
+        case 128: k_match_deep<128><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
+        case 256: k_match_deep<256><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
         default: fprintf(stderr, "[brotli_b200] unsupported bucket depth %d\n", P.depth); return false;
       }
       launches += 1;

@@ -487,6 +487,155 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
   a.best[p] = outv;
 }
 
+// Deep buckets (depth 64..256: q7..q9 and lgwin <= 16).  With one position per lane the survivors of the 4-byte filter are
+// evaluated by 4..7 active lanes on average (ncu: 10.6 of 32 threads per instruction at q9), so here the (position,
+// candidate) pairs of a whole warp are compacted and evaluated 32 at a time; results meet in a per-position atomicMax on
+// score << 16 | (255 - candidate index) << 8 | len.  "Highest score, nearest on ties" is exactly what the sequential
+// newest-first walk with strict improvement computes.  The "must be strictly longer" pre-filter uses the best of the
+// *previous* groups only (all nearer), which keeps it exact.
+template <int DEPTH>
+__global__ void __launch_bounds__(MATCH_THREADS) k_match_deep(MatchArgs a) {
+  extern __shared__ uint32_t smem[];
+  constexpr uint32_t E = MATCH_THREADS + (uint32_t)DEPTH;
+  uint32_t* s_pos = smem;
+  uint32_t* s_key = smem + E;
+  uint32_t* s_d0 = smem + 2 * E;
+  uint32_t* s_d1 = smem + 3 * E;
+  uint32_t* s_d2 = smem + 4 * E;
+  uint32_t* s_d3 = smem + 5 * E;
+  __shared__ uint16_t s_pairs[MATCH_THREADS / 32][512];
+  __shared__ uint32_t s_bestk[MATCH_THREADS / 32][32];
+  __shared__ uint32_t s_snap[MATCH_THREADS / 32][32];  // best length of the previous groups
+  __shared__ uint32_t s_far[MATCH_THREADS / 32];
+  const int64_t j0 = (int64_t)blockIdx.x * MATCH_THREADS - DEPTH;
+  for (uint32_t i = threadIdx.x; i < E; i += MATCH_THREADS) {
+    int64_t j = j0 + i;
+    uint32_t pos = 0xFFFFFFFFu, key = 0xFFFFFFFFu, w[4] = {0, 0, 0, 0};
+    if (j >= 0 && j < (int64_t)a.count) {
+      pos = a.sorted[j];
+      load16_unaligned(a.data + a.origin + pos, w);
+      key = hash_key_from_words(a.hash_type, a.key_bits, w[0], w[1]);
+    }
+    s_pos[i] = pos; s_key[i] = key; s_d0[i] = w[0]; s_d1[i] = w[1]; s_d2[i] = w[2]; s_d3[i] = w[3];
+  }
+  __syncthreads();
+  const uint32_t FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t i = threadIdx.x + (uint32_t)DEPTH;
+  const uint32_t prel = s_pos[i];
+  const bool active = !(prel == 0xFFFFFFFFu || prel < a.payload_begin);
+  const uint32_t p = a.origin + (active ? prel : 0u);
+  const uint32_t maxl = active ? bmin(a.lcap, a.n - p) : 0u;
+  const uint32_t kNone = (BRO_MIN_SCORE << 16) | 0xFFFFu;
+  s_bestk[wid][lane] = kNone;
+  s_snap[wid][lane] = 0;
+  if (lane == 0) s_far[wid] = 0;
+  __syncwarp();
+  const uint32_t key = s_key[i], m0 = s_d0[i];
+  bool done = !active || a.n - p < 8;
+  const uint32_t wbase = wid * 32u + (uint32_t)DEPTH;  // smem index of lane 0's entry
+  for (uint32_t cbase = 0; cbase < (uint32_t)DEPTH; cbase += 16) {
+    if (!__any_sync(FULL, !done)) break;
+    uint32_t mask = 0;
+    if (!done) {
+      const uint32_t bl = s_snap[wid][lane];
+      if (bl >= 4 && bl < 16) {
+        const uint32_t wsel = (2u + (bl >> 2)) * E, sh = (bl & 3u) * 8u;
+        const uint32_t mw = smem[wsel + i];
+#pragma unroll
+        for (uint32_t c = 0; c < 16; ++c) {
+          const uint32_t ci = i - 1u - cbase - c;
+          mask |= (uint32_t)((s_key[ci] == key) & (s_d0[ci] == m0) & ((((smem[wsel + ci] ^ mw) >> sh) & 0xFFu) == 0u)) << c;
+        }
+      } else {
+#pragma unroll
+        for (uint32_t c = 0; c < 16; ++c) {
+          const uint32_t ci = i - 1u - cbase - c;
+          mask |= (uint32_t)((s_key[ci] == key) & (s_d0[ci] == m0)) << c;
+        }
+      }
+      if (s_key[i - 16u - cbase] != key) done = true;  // the bucket ends inside this group
+    }
+    // compact the (lane, candidate) pairs of the warp
+    const uint32_t cnt = __popc(mask);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(FULL, incl, o);
+      if (lane >= (uint32_t)o) incl += y;
+    }
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    {
+      uint32_t off = incl - cnt, mm = mask;
+      while (mm) {
+        const uint32_t c = (uint32_t)__ffs((int)mm) - 1u;
+        mm &= mm - 1u;
+        s_pairs[wid][off++] = (uint16_t)((lane << 4) | c);
+      }
+    }
+    __syncwarp();
+    for (uint32_t k = lane; k < total; k += 32) {
+      const uint32_t pr = s_pairs[wid][k];
+      const uint32_t ln = pr >> 4, c = pr & 15u;
+      const uint32_t ie = wbase + ln;
+      const uint32_t ci = ie - 1u - cbase - c;
+      const uint32_t eprel = s_pos[ie];
+      const uint32_t ep = a.origin + eprel;
+      const uint32_t emaxl = bmin(a.lcap, a.n - ep);
+      const uint32_t backward = eprel - s_pos[ci];
+      if (backward > bmin(ep, a.max_backward)) { atomicOr(&s_far[wid], 1u << ln); continue; }
+      const uint32_t bl = s_snap[wid][ln];
+      if (bl >= 16 && bl < emaxl && a.data[ep + bl] != a.data[ep - backward + bl]) continue;  // cannot be strictly longer
+      uint32_t len;
+      uint32_t x = s_d1[ci] ^ s_d1[ie];
+      if (x) len = 4 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+      else {
+        x = s_d2[ci] ^ s_d2[ie];
+        if (x) len = 8 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+        else {
+          x = s_d3[ci] ^ s_d3[ie];
+          if (x) len = 12 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+          else {
+            len = 16;
+            const uint8_t* pa = a.data + ep;
+            const uint8_t* pb = pa - backward;
+            while (len + 8 <= emaxl) {
+              const uint64_t y = ldu64(pa + len) ^ ldu64(pb + len);
+              if (y) { len += (uint32_t)(__ffsll((long long)y) - 1) >> 3; break; }
+              len += 8;
+            }
+            if (len + 8 > emaxl) while (len < emaxl && pa[len] == pb[len]) ++len;
+          }
+        }
+      }
+      if (len > emaxl) len = emaxl;
+      const uint32_t score = score_regular(a.hash_type, len, backward);
+      atomicMax(&s_bestk[wid][ln], (score << 16) | ((255u - (cbase + c)) << 8) | len);
+    }
+    __syncwarp();
+    if (!done) {
+      const uint32_t bk = s_bestk[wid][lane];
+      if (bk != kNone) {
+        s_snap[wid][lane] = bk & 0xFFu;
+        if ((bk & 0xFFu) == maxl) done = true;  // a full-length match: nothing farther can beat it
+      }
+      if ((s_far[wid] >> lane) & 1u) done = true;  // candidates beyond the window: all older ones too
+    }
+    __syncwarp();
+  }
+  if (active) {
+    const uint32_t bk = s_bestk[wid][lane];
+    uint32_t r = 0;
+    if (bk != kNone) {
+      const uint32_t cc = 255u - ((bk >> 8) & 0xFFu);
+      r = ((prel - s_pos[i - 1u - cc]) << 8) | (bk & 0xFFu);
+    } else if (a.use_dict && a.n - p >= 8) {
+      r = dict_candidate_dev(a.dict, a.hash_type, s_d0[i], s_d1[i], s_d2[i], s_d3[i], a.data + p, a.n - p, bmin(p, a.max_backward));
+    }
+    a.best[p] = r;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Parse: one thread per unit.
 // ---------------------------------------------------------------------------------------------------
