@@ -109,6 +109,7 @@ struct B200Encoder {
   uint32_t unit = 4096, mb_units = 1024, lcap = 64;
   int use_rle_opt = 1, split = 1, ctx_model = 1, use_dict = 1;
   int num_lanes = 4;
+  int shallow_match = 1;  // branch-free candidate scan for depth 16 / 32 (0: loop version, kept for A/B measurements)
   Lane lanes[kMaxLanes];
   cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams
   DevBuf d_dict_words, d_dict_hash;
@@ -384,8 +385,14 @@ struct B200Encoder {
       mark(L, B200_ST_MATCH);
       const uint32_t mgrid = (count + MATCH_THREADS - 1) / MATCH_THREADS;
       switch (P.depth) {  // bucket depth = 1 << block_bits: 16 (q5) .. 256 (q9, and lgwin <= 16)
-        case 16: k_match<false, 16><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
-        case 32: k_match<false, 32><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
+        case 16:
+          if (shallow_match) k_match_shallow<16><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
+          else k_match<false, 16><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
+          break;
+        case 32:
+          if (shallow_match) k_match_shallow<32><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
+          else k_match<false, 32><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
+          break;
         case 64: k_match_deep<64><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
         case 128: k_match_deep<128><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
         case 256: k_match_deep<256><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
@@ -475,6 +482,7 @@ int b200_encoder_set_option(B200Encoder* e, int option, uint32_t value) {
     case B200_OPT_CTX_MODEL: e->ctx_model = (int)value; return 1;
     case B200_OPT_TIMING: e->timing = value != 0; return 1;
     case B200_OPT_DICT: e->use_dict = (int)value; return 1;
+    case B200_OPT_SHALLOW_MATCH: e->shallow_match = (int)value; return 1;
     case B200_OPT_LANES: e->num_lanes = value < 1 ? 1 : (value > (uint32_t)kMaxLanes ? kMaxLanes : (int)value); return 1;
   }
   return 0;

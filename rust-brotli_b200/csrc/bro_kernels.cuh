@@ -487,6 +487,98 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
   a.best[p] = outv;
 }
 
+// Shallow buckets (depth 16 / 32: q5, q6) -- the bench path.  ncu on the loop version (profiles/r01n): 53 % of the warp
+// instructions were the divergent per-survivor loop (23 of 32 lanes active, ~11 rounds per warp).  Here every candidate
+// whose match is shorter than 8 bytes -- the bulk on text -- is resolved branch-free inside the unrolled scan (its length
+// comes from one XOR of the second data word), and only candidates that agree on all 8 bytes go through the exact
+// (divergent) evaluation.  Result identical to the sequential newest-first walk: highest score, nearest on ties.
+template <int DEPTH>
+__global__ void __launch_bounds__(MATCH_THREADS) k_match_shallow(MatchArgs a) {
+  extern __shared__ uint32_t smem[];
+  constexpr uint32_t E = MATCH_THREADS + (uint32_t)DEPTH;
+  uint32_t* s_pos = smem;
+  uint32_t* s_key = smem + E;
+  uint32_t* s_d0 = smem + 2 * E;
+  uint32_t* s_d1 = smem + 3 * E;
+  uint32_t* s_d2 = smem + 4 * E;
+  uint32_t* s_d3 = smem + 5 * E;
+  const int64_t j0 = (int64_t)blockIdx.x * MATCH_THREADS - DEPTH;
+  for (uint32_t i = threadIdx.x; i < E; i += MATCH_THREADS) {
+    int64_t j = j0 + i;
+    uint32_t pos = 0xFFFFFFFFu, key = 0xFFFFFFFFu, w[4] = {0, 0, 0, 0};
+    if (j >= 0 && j < (int64_t)a.count) {
+      pos = a.sorted[j];
+      load16_unaligned(a.data + a.origin + pos, w);
+      key = hash_key_from_words(a.hash_type, a.key_bits, w[0], w[1]);
+    }
+    s_pos[i] = pos; s_key[i] = key; s_d0[i] = w[0]; s_d1[i] = w[1]; s_d2[i] = w[2]; s_d3[i] = w[3];
+  }
+  __syncthreads();
+  const uint32_t i = threadIdx.x + (uint32_t)DEPTH;
+  const uint32_t prel = s_pos[i];
+  if (prel == 0xFFFFFFFFu || prel < a.payload_begin) return;
+  const uint32_t p = a.origin + prel;
+  const uint32_t maxl = bmin(a.lcap, a.n - p);
+  uint32_t best_score = BRO_MIN_SCORE, best_len = 0, best_dist = 0;
+  if (a.n - p >= 8) {  // keys of the last 7 positions would depend on bytes past the range: they get no bucket match
+    const uint32_t key = s_key[i];
+    const uint32_t max_backward = bmin(p, a.max_backward);
+    const uint32_t m0 = s_d0[i], m1 = s_d1[i], m2 = s_d2[i], m3 = s_d3[i];
+    for (uint32_t cbase = 0; cbase < (uint32_t)DEPTH; cbase += 16) {
+      uint32_t mask8 = 0;
+#pragma unroll
+      for (uint32_t c = 0; c < 16; ++c) {
+        const uint32_t ci = i - 1u - cbase - c;
+        const uint32_t backward = prel - s_pos[ci];
+        const uint32_t x1 = s_d1[ci] ^ m1;
+        const bool ok = (s_key[ci] == key) & (s_d0[ci] == m0) & (backward <= max_backward);
+        mask8 |= (uint32_t)(ok & (x1 == 0u)) << c;
+        const uint32_t len = 4u + ((uint32_t)(__ffs((int)x1) - 1) >> 3);  // 4..7 when x1 != 0
+        const uint32_t score = score_regular(5, len, backward | 1u);      // H5 / H6 share the score; |1 keeps log2 defined
+        const bool better = ok & (x1 != 0u) & (score > best_score);
+        best_score = better ? score : best_score;
+        best_len = better ? len : best_len;
+        best_dist = better ? backward : best_dist;
+      }
+      // candidates that agree on 8 bytes: exact length, nearest first
+      while (mask8) {
+        const uint32_t c = (uint32_t)__ffs((int)mask8) - 1u;
+        mask8 &= mask8 - 1u;
+        const uint32_t ci = i - 1u - cbase - c;
+        const uint32_t backward = prel - s_pos[ci];
+        uint32_t len;
+        uint32_t x = s_d2[ci] ^ m2;
+        if (x) len = 8 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+        else {
+          x = s_d3[ci] ^ m3;
+          if (x) len = 12 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+          else {
+            len = 16;
+            const uint8_t* pa = a.data + p;
+            const uint8_t* pb = pa - backward;
+            while (len + 8 <= maxl) {
+              const uint64_t y = ldu64(pa + len) ^ ldu64(pb + len);
+              if (y) { len += (uint32_t)(__ffsll((long long)y) - 1) >> 3; break; }
+              len += 8;
+            }
+            if (len + 8 > maxl) while (len < maxl && pa[len] == pb[len]) ++len;
+          }
+        }
+        if (len > maxl) len = maxl;
+        const uint32_t score = score_regular(5, len, backward);
+        if (score > best_score || (score == best_score && backward < best_dist)) { best_score = score; best_len = len; best_dist = backward; }
+        if (len == maxl) break;  // nothing farther in this group can be better
+      }
+      if (best_len == maxl) break;  // nor in an older group
+      if (s_key[i - 16u - cbase] != key) break;  // the bucket ended inside this group
+    }
+  }
+  uint32_t outv = best_len ? ((best_dist << 8) | best_len) : 0u;
+  if (best_len == 0 && a.use_dict && a.n - p >= 8)  // nothing in the bucket: static dictionary (mod.rs:1797, :1942)
+    outv = dict_candidate_dev(a.dict, a.hash_type, s_d0[i], s_d1[i], s_d2[i], s_d3[i], a.data + p, a.n - p, bmin(p, a.max_backward));
+  a.best[p] = outv;
+}
+
 // Deep buckets (depth 64..256: q7..q9 and lgwin <= 16).  With one position per lane the survivors of the 4-byte filter are
 // evaluated by 4..7 active lanes on average (ncu: 10.6 of 32 threads per instruction at q9), so here the (position,
 // candidate) pairs of a whole warp are compacted and evaluated 32 at a time; results meet in a per-position atomicMax on
