@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbrotli_b200.so")
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(_HERE, "libbrotli_b200.so")  # B200_LIB: A/B builds (tools/)
 
 NUM_STAGES = 7
 STAGE_NAMES = ("sort", "match", "parse", "finalize", "split", "header", "emit")

@@ -509,7 +509,13 @@ static bool compress_range_impl(B200Encoder* e, int quality, int lgwin, uint64_t
   const size_t end = range_start + range_len;
   const size_t staged = end - base;
   const size_t need = b200_max_compressed_size(range_len) + 64;
-  const size_t nchunks = (range_len + kChunk - 1) / kChunk;
+  std::vector<std::pair<size_t, size_t>> chunks;  // (absolute start, length)
+  for (size_t done = 0; done < range_len;) {
+    const size_t len = chunk_len_at(done, range_len);
+    chunks.emplace_back(range_start + done, len);
+    done += len;
+  }
+  const size_t nchunks = chunks.size();
   const cudaMemcpyKind in_kind = device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   const cudaMemcpyKind out_kind = device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   if (!e->d_data.ensure(staged + kPad) || !e->d_out.ensure(need) || !e->ensure_totals(nchunks)) return false;
@@ -522,8 +528,7 @@ static bool compress_range_impl(B200Encoder* e, int quality, int lgwin, uint64_t
   cudaEvent_t prev_layout = nullptr;
   size_t copied = base;  // absolute position up to which the input is staged
   for (size_t k = 0; k < nchunks; ++k) {
-    const size_t s = range_start + k * (size_t)kChunk;
-    const size_t len = std::min<size_t>(kChunk, end - s);
+    const size_t s = chunks[k].first, len = chunks[k].second;
     // stage the input this chunk can see: its window halo (first chunk), its own bytes, a short look-ahead
     const size_t upto = std::min(end, s + len + kLookahead);
     if (upto > copied) {

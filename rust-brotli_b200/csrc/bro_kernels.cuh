@@ -321,7 +321,9 @@ __device__ __forceinline__ uint64_t ldu64(const uint8_t* p) {
 // ---------------------------------------------------------------------------------------------------
 // Match search over the sorted position list of one batch.
 // ---------------------------------------------------------------------------------------------------
+#ifndef MATCH_THREADS
 #define MATCH_THREADS 256
+#endif
 
 struct MatchArgs {
   const uint8_t* data;      // whole input (padded)
@@ -1101,7 +1103,10 @@ __device__ __forceinline__ uint32_t parse_unit_warp4(const EncParams& P, const u
   return ncmd;
 }
 
-__global__ void __launch_bounds__(PARSE_WARPS * 32) k_parse(Workspace W) {
+#ifndef PARSE_MIN_BLOCKS
+#define PARSE_MIN_BLOCKS 10
+#endif
+__global__ void __launch_bounds__(PARSE_WARPS * 32, PARSE_MIN_BLOCKS) k_parse(Workspace W) {
   // One parse unit per warp.
   const uint32_t u = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);
   if (u >= W.num_units) return;
