@@ -10,15 +10,14 @@
 
 // bytes per pipeline pass: one chunk = 6 metablocks of 4 MiB; with its 4 MiB window halo it is one 2^25 sort batch
 #define BRO_CHUNK_BYTES (24u << 20)
-// the first chunk of a multi-chunk range is short, so that compute starts after 8 MiB of the input have arrived
-#define BRO_FIRST_CHUNK_BYTES (8u << 20)
 
 namespace bro {
 
 // length of the chunk that starts `done` bytes into a range of `total` bytes (shared by the encoder and its CPU model)
 BRO_HD uint32_t chunk_len_at(uint64_t done, uint64_t total) {
+  // (a short first chunk, to start computing before the whole first 24 MiB are staged, was measured: e2e unchanged,
+  // HBM-resident throughput -5 % because the last chunk then no longer hides behind the others)
   const uint64_t left = total - done;
-  if (done == 0 && total > BRO_CHUNK_BYTES) return BRO_FIRST_CHUNK_BYTES;
   return (uint32_t)(left < BRO_CHUNK_BYTES ? left : BRO_CHUNK_BYTES);
 }
 
