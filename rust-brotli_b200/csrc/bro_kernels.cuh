@@ -1772,8 +1772,16 @@ __global__ void __launch_bounds__(32) k_trees(Workspace W) {
   }
   const uint32_t tree_cap = W.max_lit_trees + W.max_cmd_types + W.max_dist_types;
   HuffStoreWs* ws = &ws_s;
+  // the histogram is worked on in shared memory: the RLE smoothing and the symbol scans below are serial, and on global
+  // memory every dependent access is an L2 round trip
+  __shared__ uint32_t s_hist[704];
+  uint32_t* const ghist = hist;
+  for (uint32_t i = lane; i < A; i += 32) s_hist[i] = ghist[i];
+  __syncwarp();
+  hist = s_hist;
   if (P.use_rle_opt && lane == 0) huff_optimize_counts_for_rle(A, hist, ws->rle);
   __syncwarp();
+  for (uint32_t i = lane; i < A; i += 32) ghist[i] = s_hist[i];
   // == huff_build_and_store(), with the tree construction done by the whole warp ==
   __shared__ uint32_t s4[4];  // first four used symbols (kept in shared memory: see profiles/ notes on the local-array clobber)
   uint32_t count = 0, max_bits = 0;

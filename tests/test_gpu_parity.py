@@ -92,6 +92,16 @@ def test_multi_chunk_stream_equals_model(encoder, model):
     assert sys_decompress(ref, len(d)) == d
 
 
+def test_large_window_multi_batch(encoder, model):
+    """lgwin 24: the window (16 MiB) is most of a 2^25-position sort batch, so a 24 MiB chunk takes two batches and the second
+    chunk sees a halo longer than itself; the stream must equal the model's across both kinds of seam."""
+    from tools import datagen
+    d = datagen.enwik_like(28_000_000, seed=3)
+    c = encoder.compress(d, 5, 24)
+    assert sys_decompress(c, len(d)) == d
+    assert c == model.compress(d, 5, 24)[0]
+
+
 def test_structured_logs_size_parity(encoder, oracle):
     """Record-structured JSON logs lean on the distance cache: the warm-up in front of every parse unit keeps the size
     within +0.5 % of the reference restatement (it was +1.4 % with units that start from an unknown cache)."""
