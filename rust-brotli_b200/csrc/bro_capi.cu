@@ -15,6 +15,8 @@
 
 namespace {
 
+constexpr size_t BRO_CHUNK_BYTES_CAPI = (size_t)24 << 20;  // = BRO_CHUNK_BYTES of the device encoder
+
 struct EncoderParams {  // the subset of BrotliEncoderParams (backward_references/mod.rs:71-125) this path consumes
   int quality = 11;     // defaults: encode.rs:318-357
   int lgwin = 22;
@@ -69,11 +71,17 @@ B200Encoder* shared_encoder(int device, std::mutex** mu) {
 
 }  // namespace
 
+// Stream state.  Input is buffered on the host; PROCESS turns it into output whenever kStreamPieceBytes are pending (the
+// reference also emits as its blocks fill, encode.rs:2873-2995), FLUSH / FINISH emit whatever is pending.  Pieces end
+// byte aligned (padding metablock), and only the last 2^lgwin bytes in front of the unflushed part are kept as match
+// window, so a stream of any length needs a bounded buffer.
+constexpr size_t kStreamPieceBytes = (size_t)4 * BRO_CHUNK_BYTES_CAPI;
 struct BrotliEncoderStateStruct {
   EncoderParams params;
   B200Encoder* enc = nullptr;
-  std::vector<uint8_t> input;   // everything consumed so far (the device sees it as the match window)
-  size_t flushed = 0;           // bytes of `input` already turned into output
+  std::vector<uint8_t> input;   // stream bytes [base, base + input.size())
+  uint64_t base = 0;            // absolute stream offset of input[0] (multiple of 4096)
+  uint64_t flushed = 0;         // absolute offset up to which the stream has been turned into output
   std::vector<uint8_t> output;  // produced, not yet taken
   size_t out_pos = 0;
   bool started = false, finished = false, header_written = false;
@@ -125,8 +133,9 @@ BROTLI_BOOL BrotliEncoderSetParameter(BrotliEncoderState* s, BrotliEncoderParame
   return apply_param(s->params, (int)p, value) ? BROTLI_TRUE : BROTLI_FALSE;
 }
 
-static bool state_emit(BrotliEncoderStateStruct* s, bool last) {
-  const size_t start = s->flushed, len = s->input.size() - start;
+// Compresses the stream bytes [flushed, upto) and appends the result to the output queue.
+static bool state_emit(BrotliEncoderStateStruct* s, bool last, uint64_t upto) {
+  const uint64_t start = s->flushed, len = upto - start;
   const bool first = !s->header_written;
   if (len == 0) {
     if (last) {
@@ -141,13 +150,26 @@ static bool state_emit(BrotliEncoderStateStruct* s, bool last) {
   s->output.resize(old + cap);
   b200_encoder_set_option(s->enc, B200_OPT_CTX_MODEL, s->params.disable_ctx ? 0 : 1);
   b200_encoder_set_option(s->enc, B200_OPT_DICT, s->params.no_dictionary ? 0 : 1);
-  uint64_t hint = s->params.size_hint ? s->params.size_hint : s->input.size();
-  int ok = b200_encoder_compress_range(s->enc, s->params.quality, s->params.lgwin, hint, s->input.data(), s->input.size(), start, len,
-                                       first ? 1 : 0, last ? 1 : 0, last ? 0 : 1, s->output.data() + old, cap, &got, 0);
+  uint64_t hint = s->params.size_hint ? s->params.size_hint : s->base + s->input.size();
+  // positions are relative to `base`: once a prefix has been dropped at least a full window precedes `start`, so the
+  // window limit min(position, 2^lgwin - 16) is the same in both coordinate systems
+  int ok = b200_encoder_compress_range(s->enc, s->params.quality, s->params.lgwin, hint, s->input.data(), (size_t)(upto - s->base),
+                                       (size_t)(start - s->base), (size_t)len, first ? 1 : 0, last ? 1 : 0, last ? 0 : 1,
+                                       s->output.data() + old, cap, &got, 0);
   if (!ok) { s->output.resize(old); return false; }
   s->output.resize(old + got);
-  s->flushed = s->input.size();
+  s->flushed = upto;
   s->header_written = true;
+  // keep only the match window in front of the unflushed part
+  int lw = s->params.lgwin < 10 ? 10 : (s->params.lgwin > 24 ? 24 : s->params.lgwin);
+  const uint64_t window = ((uint64_t)1 << lw) + 65536;
+  if (s->flushed > s->base + window) {
+    const uint64_t keep_from = (s->flushed - window) & ~(uint64_t)4095;
+    if (keep_from > s->base) {
+      s->input.erase(s->input.begin(), s->input.begin() + (size_t)(keep_from - s->base));
+      s->base = keep_from;
+    }
+  }
   return true;
 }
 
@@ -162,11 +184,15 @@ BROTLI_BOOL BrotliEncoderCompressStream(BrotliEncoderState* s, BrotliEncoderOper
     *next_in += *available_in;
     *available_in = 0;
   }
-  if (op == BROTLI_OPERATION_FLUSH && s->flushed < s->input.size()) {
-    if (!state_emit(s, false)) return BROTLI_FALSE;
+  const uint64_t end = s->base + s->input.size();
+  while (op == BROTLI_OPERATION_PROCESS && end - s->flushed >= 2 * kStreamPieceBytes) {  // keep one piece back for FINISH
+    if (!state_emit(s, false, s->flushed + kStreamPieceBytes)) return BROTLI_FALSE;
+  }
+  if (op == BROTLI_OPERATION_FLUSH && s->flushed < end) {
+    if (!state_emit(s, false, end)) return BROTLI_FALSE;
   } else if (op == BROTLI_OPERATION_FINISH && !s->finished) {
     s->started = true;
-    if (!state_emit(s, true)) return BROTLI_FALSE;
+    if (!state_emit(s, true, end)) return BROTLI_FALSE;
     s->finished = true;
   }
   size_t avail = s->output.size() - s->out_pos;

@@ -92,6 +92,25 @@ def test_multi_chunk_stream_equals_model(encoder, model):
     assert sys_decompress(ref, len(d)) == d
 
 
+def test_long_stream_is_emitted_in_pieces():
+    """CompressorWriter fed 230 MB in 8 MiB writes: PROCESS emits byte-aligned 96 MiB pieces while input keeps arriving and
+    keeps only the match window of what is already emitted (bounded host buffer); the concatenation is one valid stream."""
+    import rust_brotli_b200 as rb
+    from tools import datagen
+    base = datagen.enwik_like(23_000_000, seed=5)
+    sink = io.BytesIO()
+    w = rb.CompressorWriter(sink, 4096, 5, 22)
+    emitted_before_close = 0
+    for rep in range(10):
+        for o in range(0, len(base), 8 << 20):
+            w.write(base[o:o + (8 << 20)])
+        emitted_before_close = sink.tell()
+    w.close()
+    assert emitted_before_close > 0, "no output before FINISH"
+    out = sink.getvalue()
+    assert sys_decompress(out, 10 * len(base)) == base * 10
+
+
 def test_large_window_multi_batch(encoder, model):
     """lgwin 24: the window (16 MiB) is most of a 2^25-position sort batch, so a 24 MiB chunk takes two batches and the second
     chunk sees a halo longer than itself; the stream must equal the model's across both kinds of seam."""
