@@ -229,3 +229,46 @@ def test_device_resident_io(encoder):
     c = bytes(t_out[:n].cpu().numpy())
     assert sys_decompress(c, len(d)) == d
     assert c == encoder.compress(d, 5, 22)
+
+
+# ---- BASELINE.json configs at their full per-GPU sizes: size-independent properties (round trip, size bounds) ----
+
+def test_config3_random10k_tiled_1gb(encoder):
+    """configs[2]: random_org_10k.bin tiled to 1 GB, q5, lgwin 22 (period 10 000 B < window: the long-copy path; 42 chunks)."""
+    from tools import datagen
+    d = datagen.tiled(golden_bytes("random_org_10k.bin"), 1_000_000_000)
+    c = encoder.compress(d, 5, 22)
+    assert len(c) < 20_000  # one period of literals + one long copy per 4 MiB metablock
+    assert hashlib.sha256(sys_decompress(c, len(d))).digest() == hashlib.sha256(d).digest()
+
+
+def test_config3b_incompressible_256mb(encoder):
+    """PCG bytes: every metablock is stored raw; size = input + a few bytes per metablock."""
+    from tools import datagen
+    d = datagen.pcg_random(256_000_000)
+    c = encoder.compress(d, 5, 22)
+    assert len(d) < len(c) <= len(d) + 8 * (len(d) // (4 << 20) + 2)
+    assert sys_decompress(c, len(d)) == d
+
+
+def test_config4_json_q9_one_shard_512mib():
+    """configs[3]: JSON logs, q9, lgwin 22, compress_multi; one GPU's share (512 MiB) split into 8 byte-aligned shards that
+    concatenate with memcpy (the reference needs BroCatli for that step)."""
+    import rust_brotli_b200 as rb
+    from tools import datagen
+    d = datagen.json_logs(64_000_000) * 8
+    d = d + d[:(512 << 20) - len(d)]
+    assert len(d) == 512 << 20
+    c = rb.compress_multi(rb.BrotliEncoderParams(quality=9, lgwin=22), d, 8)
+    assert len(c) < 0.2 * len(d)
+    assert hashlib.sha256(sys_decompress(c, len(d))).digest() == hashlib.sha256(d).digest()
+
+
+def test_config5_quickfox_tiled_512mib_q11_lgwin24(encoder):
+    """configs[4]: quickfox_repeated tiled to 512 MiB, quality 11, lgwin 24.  q >= 10 runs the q9 device path (H10 / Zopfli are
+    not built): the stream must still be valid and tiny."""
+    from tools import datagen
+    d = datagen.tiled(golden_bytes("quickfox_repeated"), 512 << 20)
+    c = encoder.compress(d, 11, 24)
+    assert len(c) < 4096
+    assert hashlib.sha256(sys_decompress(c, len(d))).digest() == hashlib.sha256(d).digest()
