@@ -321,12 +321,16 @@ def main():
                        "sharding": "compress_multi split, one shard per GPU, 4 MiB left halo, byte-aligned seams"},
             "compressed_bytes": int(float(tot[0])), "ratio": round(float(tot[0]) / total_in, 5),
             "stage_ms": stage_ms,
-            "roofline": {"bound": "hbm", "kernel": "k_match", "achieved": round(achieved, 1) if achieved else None, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_match_shallow<16> (match finder, SURVEY 8d)", "achieved": round(achieved, 1) if achieved else None, "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None, "traffic": NCU_MATCH_DRAM_BYTES_PER_LAUNCH,
                          "traffic_source": NCU_MATCH_SOURCE,
                          "peak_source": peak_src, "algorithmic_bytes_per_position": ALG_BYTES_PER_POS_MATCH,
                          "launch_ms": round(match_ms / max(1, -(-NB // CHUNK_BYTES)), 4),
                          "timed": "CUDA events on the launching stream, chunks serialised on one lane (K extra steps after the value loop)"},
+            # the parse has the larger share of the step (profiles/r01n: 28 % vs 21 %) but is latency / issue bound, not a memory kernel
+            "roofline_parse": {"kernel": "k_parse", "algorithmic_bytes_per_position": 6.8,
+                               "achieved": round(6.8 * NB / (stage_acc.get("parse", 0.0) / args.steps * 1e-3) / 1e9, 1) if stage_acc.get("parse") else None,
+                               "unit": "GB/s", "note": "1 B input + 4 B best[] + 12 B per command (0.15 commands / byte)"},
             "cpu_baseline": cpu,
             "e2e": {"value": round(e2e, 1), "unit": "MB/s", "h2d_bytes_per_step": len(local), "d2h_bytes_per_step": int(n_e2e)},
             "gpu_launches": launches, "clocks": clocks,

@@ -388,11 +388,11 @@ struct B200Encoder {
       switch (P.depth) {  // bucket depth = 1 << block_bits: 16 (q5) .. 256 (q9, and lgwin <= 16)
         case 16:
           if (shallow_match) k_match_shallow<16><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
-          else k_match<false, 16><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
+          else k_match<16><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
           break;
         case 32:
           if (shallow_match) k_match_shallow<32><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
-          else k_match<false, 32><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
+          else k_match<32><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
           break;
         case 64: k_match_deep<64><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
         case 128: k_match_deep<128><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;

@@ -383,11 +383,10 @@ __device__ __forceinline__ void load16_unaligned(const uint8_t* p, uint32_t* w) 
 }
 
 // dynamic shared memory: (MATCH_THREADS + depth) entries x 6 words.
-// PREFILTER (deep buckets, q7..q9): a farther candidate only wins if it is strictly longer, so it is rejected on the byte at
-// index best_len before the full comparison (the reference's cur[best_len] != prev[best_len] test, mod.rs:1765-1773);
-// same result, and for the shallow q5/q6 buckets the extra branch costs more than it saves.
+// Loop version: one position per lane walks its surviving candidates, nearest first (the direct form of the reference's
+// bucket walk).  Kept as the A/B baseline of k_match_shallow (B200_OPT_SHALLOW_MATCH = 0); deep buckets use k_match_deep.
 // DEPTH = bucket depth (compile time: every shared-memory array offset becomes an immediate).
-template <bool PREFILTER, int DEPTH>
+template <int DEPTH>
 __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
   extern __shared__ uint32_t smem[];
   constexpr uint32_t E = MATCH_THREADS + (uint32_t)DEPTH;
@@ -423,21 +422,10 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
     for (uint32_t cbase = 0; cbase < (uint32_t)DEPTH && !done; cbase += 16) {
       // phase 1 (branch-free, unrolled): which of the next 16 older entries share the bucket key and the first 4 bytes
       uint32_t mask = 0;
-      if (PREFILTER && best_len >= 4 && best_len < 16) {
-        // deep buckets: once a match is known, a farther candidate must also agree on the byte at index best_len
-        const uint32_t wsel = (2u + (best_len >> 2)) * E, sh = (best_len & 3u) * 8u;
-        const uint32_t mw = smem[wsel + i];
 #pragma unroll
-        for (uint32_t c = 0; c < 16; ++c) {
-          const uint32_t ci = i - 1u - cbase - c;
-          mask |= (uint32_t)((s_key[ci] == key) & (s_d0[ci] == m0) & ((((smem[wsel + ci] ^ mw) >> sh) & 0xFFu) == 0u)) << c;
-        }
-      } else {
-#pragma unroll
-        for (uint32_t c = 0; c < 16; ++c) {
-          const uint32_t ci = i - 1u - cbase - c;
-          mask |= (uint32_t)((s_key[ci] == key) & (s_d0[ci] == m0)) << c;
-        }
+      for (uint32_t c = 0; c < 16; ++c) {
+        const uint32_t ci = i - 1u - cbase - c;
+        mask |= (uint32_t)((s_key[ci] == key) & (s_d0[ci] == m0)) << c;
       }
       if (s_key[i - 16u - cbase] != key) done = true;  // the bucket ends inside this group: nothing older can match
       // phase 2: full evaluation of the survivors, nearest first
@@ -447,13 +435,6 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
         const uint32_t ci = i - 1u - cbase - c;
         const uint32_t backward = prel - s_pos[ci];
         if (backward > max_backward) { done = true; break; }
-        if (PREFILTER && best_len >= 4) {
-          if (best_len < 16) {
-            const uint32_t wsel = (2u + (best_len >> 2)) * E;
-            const uint32_t xb = smem[wsel + ci] ^ smem[wsel + i];
-            if ((xb >> ((best_len & 3u) * 8u)) & 0xFFu) continue;
-          } else if (a.data[p + best_len] != a.data[p - backward + best_len]) continue;
-        }
         uint32_t len;
         uint32_t x = s_d1[ci] ^ m1;
         if (x) len = 4 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
