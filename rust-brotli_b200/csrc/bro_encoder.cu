@@ -139,6 +139,7 @@ struct B200Encoder {
     CUDA_OK(cudaMemcpy(d_dict_words.p, kDictData, sizeof(kDictData), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(d_dict_hash.p, kDictHash, sizeof(kDictHash), cudaMemcpyHostToDevice));
     CUDA_OK(cudaDeviceSetLimit(cudaLimitStackSize, 4096));
+    CUDA_OK(cudaFuncSetAttribute(k_split_greedy, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_SMEM_WORDS * 4));
     for (int i = 0; i < B200_NUM_STAGES; ++i) stage_ms[i] = 0;
     ok = true;
     return true;
@@ -417,7 +418,7 @@ struct B200Encoder {
     mark(L, B200_ST_SPLIT);
     {
       dim3 g(W.num_mb, 3);
-      if (P.split) k_split_greedy<<<g, SPLIT_THREADS, 0, stream>>>(W);
+      if (P.split) k_split_greedy<<<g, SPLIT_THREADS, SPLIT_SMEM_WORDS * 4, stream>>>(W);
       else k_split_simple<<<g, 512, 0, stream>>>(W);
     }
     mark(L, B200_ST_HEADER);

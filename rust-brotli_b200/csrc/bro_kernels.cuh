@@ -1546,13 +1546,19 @@ __global__ void __launch_bounds__(512) k_split_simple(Workspace W) {
 #define SPLIT_THREADS 512
 #define SPLIT_WARPS (SPLIT_THREADS / 32)
 
+// The three live histograms (pending block, last and second-last block type) stay in shared memory; the per-type slots
+// in global memory are written through whenever a type's histogram changes and are never read back.  With literal
+// contexts each warp owns one context, so a FinishBlock step costs one warp reduction instead of one per context.
+#define SPLIT_SMEM_WORDS (3 * 13 * 256)
 __global__ void __launch_bounds__(SPLIT_THREADS) k_split_greedy(Workspace W) {
-  __shared__ uint64_t s_part[13][3][SPLIT_WARPS];   // sum c*log2(c) partials: pending, pending+last0, pending+last1
-  __shared__ uint32_t s_cnt[13][3][SPLIT_WARPS];    // total counts partials
+  extern __shared__ uint32_t s_hist3[];             // [3][HA]
+  __shared__ uint64_t s_part[3][SPLIT_WARPS];       // nctx == 1: sum c*log2(c) partials of pending, pending+last0, pending+last1
+  __shared__ uint32_t s_cnt[3][SPLIT_WARPS];
   __shared__ uint64_t s_e[3][13];
   __shared__ SplitState st;
   __shared__ int s_action;
-  __shared__ uint32_t s_nblocks, s_pending_slot;
+  __shared__ uint32_t s_nblocks, s_new_type;
+  __shared__ uint32_t s_ic, s_i0, s_i1;             // buffer of the pending / last / second-last histogram (i0 may equal i1)
   const uint32_t m = blockIdx.x;
   const CatInfo c = cat_info(W, m, (int)blockIdx.y);
   const uint32_t A = c.A, nctx = c.nctx, HA = nctx * A;
@@ -1562,8 +1568,9 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split_greedy(Workspace W) {
     memset(&st, 0, sizeof(st));
     st.target_block_size = c.min_block;
     s_nblocks = 0;
+    s_ic = 0; s_i0 = 1; s_i1 = 1;
   }
-  for (uint32_t i = threadIdx.x; i < HA; i += SPLIT_THREADS) c.hist[i] = 0;  // pending slot 0
+  for (uint32_t i = threadIdx.x; i < 3 * HA; i += SPLIT_THREADS) s_hist3[i] = 0;
   __syncthreads();
   uint32_t consumed = 0;
   for (;;) {
@@ -1572,9 +1579,9 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split_greedy(Workspace W) {
     const bool is_final = remaining < target;   // the last call takes whatever is left (possibly nothing)
     const uint32_t take = is_final ? remaining : target;
     const uint32_t nb = st.num_blocks;
-    uint32_t* cur = c.hist + (size_t)st.num_types * HA;
-    const uint32_t* l0 = c.hist + (size_t)st.last_type[0] * HA;
-    const uint32_t* l1 = c.hist + (size_t)st.last_type[1] * HA;
+    uint32_t* cur = s_hist3 + s_ic * HA;
+    const uint32_t* l0 = s_hist3 + s_i0 * HA;
+    const uint32_t* l1 = s_hist3 + s_i1 * HA;
     for (uint32_t i = threadIdx.x; i < take; i += SPLIT_THREADS) {
       uint32_t sv = c.syms[consumed + i];
       uint32_t sym = nctx == 1 ? sv : (sv & 0xFFu) + (sv >> 8) * A;
@@ -1582,14 +1589,38 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split_greedy(Workspace W) {
     }
     __syncthreads();
     consumed += take;
-    for (uint32_t cx = 0; cx < nctx; ++cx) {
+    if (nctx > 1) {  // A == 256: warp cx reduces context cx
+      if (wid < nctx) {
+        const uint32_t cx = wid;
+        uint64_t a0 = 0, a1 = 0, a2 = 0;
+        uint32_t t0 = 0, t1 = 0, t2 = 0;
+#pragma unroll
+        for (uint32_t r = 0; r < 8; ++r) {
+          const uint32_t k = cx * 256u + r * 32u + lane;
+          const uint32_t v = cur[k];
+          if (v) { a0 += xlog2x_q16(lut, v); t0 += v; }
+          if (nb) {
+            const uint32_t v0 = v + l0[k], v1 = v + l1[k];
+            if (v0) { a1 += xlog2x_q16(lut, v0); t1 += v0; }
+            if (v1) { a2 += xlog2x_q16(lut, v1); t2 += v1; }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+          a2 += __shfl_xor_sync(0xffffffffu, a2, o); t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+          t1 += __shfl_xor_sync(0xffffffffu, t1, o); t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+        }
+        if (lane < 3) s_e[lane][cx] = bits_entropy_q16(lane == 0 ? a0 : (lane == 1 ? a1 : a2), lane == 0 ? t0 : (lane == 1 ? t1 : t2), lut);
+      }
+    } else {
       uint64_t a0 = 0, a1 = 0, a2 = 0;
       uint32_t t0 = 0, t1 = 0, t2 = 0;
       for (uint32_t k = threadIdx.x; k < A; k += SPLIT_THREADS) {
-        uint32_t v = cur[cx * A + k];
+        const uint32_t v = cur[k];
         if (v) { a0 += xlog2x_q16(lut, v); t0 += v; }
         if (nb) {
-          uint32_t v0 = v + l0[cx * A + k], v1 = v + l1[cx * A + k];
+          const uint32_t v0 = v + l0[k], v1 = v + l1[k];
           if (v0) { a1 += xlog2x_q16(lut, v0); t1 += v0; }
           if (v1) { a2 += xlog2x_q16(lut, v1); t2 += v1; }
         }
@@ -1601,42 +1632,55 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split_greedy(Workspace W) {
         t1 += __shfl_down_sync(0xffffffffu, t1, o); t2 += __shfl_down_sync(0xffffffffu, t2, o);
       }
       if (lane == 0) {
-        s_part[cx][0][wid] = a0; s_part[cx][1][wid] = a1; s_part[cx][2][wid] = a2;
-        s_cnt[cx][0][wid] = t0; s_cnt[cx][1][wid] = t1; s_cnt[cx][2][wid] = t2;
+        s_part[0][wid] = a0; s_part[1][wid] = a1; s_part[2][wid] = a2;
+        s_cnt[0][wid] = t0; s_cnt[1][wid] = t1; s_cnt[2][wid] = t2;
       }
-    }
-    __syncthreads();
-    if (threadIdx.x < 3 * nctx) {
-      const uint32_t cx = threadIdx.x / 3, q = threadIdx.x % 3;
-      uint64_t a = 0;
-      uint32_t t = 0;
-      for (int w = 0; w < SPLIT_WARPS; ++w) { a += s_part[cx][q][w]; t += s_cnt[cx][q][w]; }
-      s_e[q][cx] = bits_entropy_q16(a, t, lut);
+      __syncthreads();
+      if (threadIdx.x < 3) {
+        const uint32_t q = threadIdx.x;
+        uint64_t a = 0;
+        uint32_t t = 0;
+        for (int w = 0; w < SPLIT_WARPS; ++w) { a += s_part[q][w]; t += s_cnt[q][w]; }
+        s_e[q][0] = bits_entropy_q16(a, t, lut);
+      }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
       uint32_t bs = take < c.min_block ? c.min_block : take;
       uint32_t old_types = st.num_types;
-      s_pending_slot = old_types;
       SplitAction act = split_decide(st, nctx, c.max_types, (uint64_t)c.thr_bits << 16, c.min_block, s_e[0], s_e[1], s_e[2]);
       s_action = (int)act;
       uint32_t b = s_nblocks;
-      if (act == SPLIT_FIRST) { c.types[b] = 0; c.lengths[b] = bs; s_nblocks = b + 1; }
-      else if (act == SPLIT_NEW_TYPE) { c.types[b] = (uint8_t)old_types; c.lengths[b] = bs; s_nblocks = b + 1; }
+      if (act == SPLIT_FIRST) { c.types[b] = 0; c.lengths[b] = bs; s_nblocks = b + 1; s_new_type = 0; }
+      else if (act == SPLIT_NEW_TYPE) { c.types[b] = (uint8_t)old_types; c.lengths[b] = bs; s_nblocks = b + 1; s_new_type = old_types; }
       else if (act == SPLIT_SECOND_LAST) { c.types[b] = (uint8_t)st.last_type[0]; c.lengths[b] = bs; s_nblocks = b + 1; }
       else { c.lengths[b - 1] += bs; }
     }
     __syncthreads();
     {
       const int act = s_action;
-      uint32_t* pend = c.hist + (size_t)s_pending_slot * HA;
+      const uint32_t ic = s_ic, i0 = s_i0, i1 = s_i1;
       if (act == SPLIT_FIRST || act == SPLIT_NEW_TYPE) {
-        uint32_t* np = c.hist + (size_t)st.num_types * HA;  // new pending slot
-        for (uint32_t i = threadIdx.x; i < HA; i += SPLIT_THREADS) np[i] = 0;
+        // the pending histogram becomes block type s_new_type: write it through, rotate the roles, take a free buffer
+        uint32_t* g = c.hist + (size_t)s_new_type * HA;
+        const uint32_t ni1 = act == SPLIT_FIRST ? ic : i0, ni0 = ic;
+        uint32_t nic = 0;
+        while (nic == ni0 || nic == ni1) ++nic;
+        uint32_t* np = s_hist3 + nic * HA;
+        for (uint32_t i = threadIdx.x; i < HA; i += SPLIT_THREADS) { g[i] = cur[i]; np[i] = 0; }
+        __syncthreads();
+        if (threadIdx.x == 0) { s_ic = nic; s_i0 = ni0; s_i1 = ni1; }
       } else {
-        // merge pending into the (new) last histogram; after SPLIT_SECOND_LAST last_type[0] is the old second-last
-        uint32_t* dst = c.hist + (size_t)st.last_type[0] * HA;
-        for (uint32_t i = threadIdx.x; i < HA; i += SPLIT_THREADS) { dst[i] += pend[i]; pend[i] = 0; }
+        // merge the pending histogram into the (new) last type: after SPLIT_SECOND_LAST that is the old second-last
+        const uint32_t ni0 = act == SPLIT_SECOND_LAST ? i1 : i0, ni1 = act == SPLIT_SECOND_LAST ? i0 : i1;
+        uint32_t* dst = s_hist3 + ni0 * HA;
+        uint32_t* g = c.hist + (size_t)st.last_type[0] * HA;
+        for (uint32_t i = threadIdx.x; i < HA; i += SPLIT_THREADS) {
+          const uint32_t v = dst[i] + cur[i];
+          dst[i] = v; g[i] = v; cur[i] = 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { s_i0 = ni0; s_i1 = ni1; }
       }
     }
     __syncthreads();
