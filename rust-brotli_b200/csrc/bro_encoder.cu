@@ -85,14 +85,14 @@ struct Lane {
   cudaStream_t stream = nullptr;
   DevBuf d_sortA, d_sortB, d_hist, d_digit, d_best, d_raw, d_unit, d_cmds, d_cmd_bits, d_lit_syms, d_cmd_syms, d_dist_syms,
       d_mb, d_split_u8, d_split_u32, d_split_counts, d_hist_lit, d_hist_cmd, d_hist_dist, d_split_codes, d_codes_u8,
-      d_codes_u16, d_hdr, d_huff_ws, d_ctxmap_ws, d_tree_ws, d_tree_bits, d_tree_nbits, d_cmd_tile, d_long_tab, d_seg_bits;
+      d_codes_u16, d_hdr, d_huff_ws, d_ctxmap_ws, d_tree_ws, d_tree_bits, d_tree_nbits, d_cmd_tile, d_long_tab, d_seg_bits, d_sect_bits, d_sect_nbits;
   EventPool marks;  // timing marks: (event, stage that starts there); -1 ends the last stage
   std::vector<int> mark_stage;
   void release() {
     DevBuf* all[] = {&d_sortA, &d_sortB, &d_hist, &d_digit, &d_best, &d_raw, &d_unit, &d_cmds, &d_cmd_bits, &d_lit_syms,
                      &d_cmd_syms, &d_dist_syms, &d_mb, &d_split_u8, &d_split_u32, &d_split_counts, &d_hist_lit, &d_hist_cmd,
                      &d_hist_dist, &d_split_codes, &d_codes_u8, &d_codes_u16, &d_hdr, &d_huff_ws, &d_ctxmap_ws, &d_tree_ws,
-                     &d_tree_bits, &d_tree_nbits, &d_cmd_tile, &d_long_tab, &d_seg_bits};
+                     &d_tree_bits, &d_tree_nbits, &d_cmd_tile, &d_long_tab, &d_seg_bits, &d_sect_bits, &d_sect_nbits};
     for (auto* b : all) b->release();
     marks.destroy();
     if (stream) cudaStreamDestroy(stream);
@@ -244,6 +244,7 @@ struct B200Encoder {
     const size_t tree_cap = (size_t)W->max_lit_trees + W->max_cmd_types + W->max_dist_types;
     if (!L.d_tree_bits.ensure((size_t)NM * tree_cap * TREE_SLOT_BYTES)) return false;
     if (!L.d_tree_nbits.ensure((size_t)NM * tree_cap * 4)) return false;
+    if (!L.d_sect_bits.ensure((size_t)NM * HDR_SECTIONS * SECT_BYTES) || !L.d_sect_nbits.ensure((size_t)NM * HDR_SECTIONS * 4)) return false;
     // sort scratch
     const uint32_t nb = std::min<uint64_t>((uint64_t)c + (1ull << P.lgwin) + 4096, kBatchMax);
     const uint32_t tiles = (nb + SORT_TILE - 1) / SORT_TILE;
@@ -293,6 +294,8 @@ struct B200Encoder {
     W->tree_ws = L.d_tree_ws.as<HuffStoreWs>();
     W->tree_bits = L.d_tree_bits.as<uint8_t>();
     W->tree_nbits = L.d_tree_nbits.as<uint32_t>();
+    W->sect_bits = L.d_sect_bits.as<uint8_t>();
+    W->sect_nbits = L.d_sect_nbits.as<uint32_t>();
     W->total_bits = d_total.as<uint64_t>();
     return true;
   }
@@ -423,7 +426,7 @@ struct B200Encoder {
     }
     mark(L, B200_ST_HEADER);
     {
-      dim3 g(W.max_lit_trees + W.max_cmd_types + W.max_dist_types, W.num_mb);
+      dim3 g(W.max_lit_trees + W.max_cmd_types + W.max_dist_types + HDR_SECTIONS, W.num_mb);
       k_trees<<<g, 32, 0, stream>>>(W);
     }
     k_header<<<W.num_mb, 32, 0, stream>>>(W);

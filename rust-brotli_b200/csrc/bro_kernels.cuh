@@ -98,6 +98,8 @@ struct Workspace {
   HuffStoreWs* tree_ws;   // [num_mb][tree_cap]
   uint8_t* tree_bits;     // [num_mb][tree_cap][TREE_SLOT_BYTES]
   uint32_t* tree_nbits;   // [num_mb][tree_cap]
+  uint8_t* sect_bits;     // [num_mb][HDR_SECTIONS][SECT_BYTES] header sections built beside the trees
+  uint32_t* sect_nbits;   // [num_mb][HDR_SECTIONS]
   uint32_t* ctxmap_ws;    // [num_mb][max_lit_types * 64]
   // output
   uint32_t* out;          // zero-initialised words
@@ -1700,6 +1702,10 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split_greedy(Workspace W) {
 // the metablock prologue (block-split codes, context maps) and splices the per-tree descriptions behind it.
 // ---------------------------------------------------------------------------------------------------
 #define TREE_SLOT_BYTES 1536
+// header sections that depend only on the block splits are serialised by extra blocks of k_trees, concurrently with
+// the prefix codes: 0..2 block-split codes (literal, command, distance), 3 literal context map, 4 distance context map
+#define HDR_SECTIONS 5
+#define SECT_BYTES 16384
 
 // Warp-cooperative huff_create_tree(): the (count asc, symbol desc) order is a total order, so any correct sort gives
 // the reference's node order -- here a bitonic sort of 64-bit keys in shared memory by all 32 lanes; the two-queue
@@ -1782,6 +1788,26 @@ __global__ void __launch_bounds__(32) k_trees(Workspace W) {
   const uint32_t* cnt = W.split_counts + (size_t)m * 6;
   const uint32_t nlit = cnt[1] * nctx, ncmd = cnt[3], ndist = cnt[5];
   uint32_t t = blockIdx.x;
+  const uint32_t tree_cap_total = W.max_lit_trees + W.max_cmd_types + W.max_dist_types;
+  if (t >= tree_cap_total) {  // header section (serial code, one lane)
+    const uint32_t k = t - tree_cap_total;
+    if (lane != 0 || k >= HDR_SECTIONS) return;
+    BitWriter sw;
+    sw.init(W.sect_bits + ((size_t)m * HDR_SECTIONS + k) * SECT_BYTES);
+    SplitCode* sc = W.split_codes + (size_t)m * 3;
+    if (k < 3) {
+      SplitView v = make_view(W, m, (int)k);
+      store_block_split_code(sw, v, sc + k, &ws_s);
+    } else if (k == 3) {
+      if (mb.ctx_map_id == CTXMAP_NONE) store_trivial_context_map(sw, cnt[1], 6, &ws_s);
+      else store_static_literal_context_map(sw, cnt[1], mb.ctx_map_id, W.ctxmap_ws + (size_t)m * 256 * 64, &ws_s);
+    } else {
+      store_trivial_context_map(sw, cnt[5], 2, &ws_s);
+    }
+    sw.flush_partial();
+    W.sect_nbits[(size_t)m * HDR_SECTIONS + k] = (uint32_t)sw.bit_pos();
+    return;
+  }
   if (t >= nlit + ncmd + ndist) return;
   const uint32_t slot = t;
   uint32_t* hist; uint8_t* depth; uint16_t* code; uint32_t A;
@@ -1876,16 +1902,14 @@ __global__ void __launch_bounds__(32) k_header(Workspace W) {
   BitWriter bw;
   bw.init(W.hdr + (size_t)m * W.hdr_cap);
   store_compressed_metablock_header(bw, false, mb.len);
-  SplitCode* sc = W.split_codes + (size_t)m * 3;
-  store_block_split_code(bw, lv, sc + 0, ws);
-  store_block_split_code(bw, cv, sc + 1, ws);
-  store_block_split_code(bw, dv, sc + 2, ws);
+  const uint8_t* sect = W.sect_bits + (size_t)m * HDR_SECTIONS * SECT_BYTES;
+  const uint32_t* snb = W.sect_nbits + (size_t)m * HDR_SECTIONS;
+  for (uint32_t k = 0; k < 3; ++k) append_bits(bw, sect + (size_t)k * SECT_BYTES, snb[k]);  // block-split codes
   bw.put(2, 0);
   bw.put(4, 0);
   for (uint32_t i = 0; i < lv.num_types; ++i) bw.put(2, 2);
-  if (mb.ctx_map_id == CTXMAP_NONE) store_trivial_context_map(bw, lv.num_types, 6, ws);
-  else store_static_literal_context_map(bw, lv.num_types, mb.ctx_map_id, W.ctxmap_ws + (size_t)m * 256 * 64, ws);
-  store_trivial_context_map(bw, dv.num_types, 2, ws);
+  append_bits(bw, sect + (size_t)3 * SECT_BYTES, snb[3]);  // literal context map
+  append_bits(bw, sect + (size_t)4 * SECT_BYTES, snb[4]);  // distance context map
   const uint32_t tree_cap = W.max_lit_trees + W.max_cmd_types + W.max_dist_types;
   const uint32_t ntrees = lv.num_types * nctx + cv.num_types + dv.num_types;
   for (uint32_t t = 0; t < ntrees; ++t)
