@@ -1384,7 +1384,7 @@ __global__ void __launch_bounds__(256) k_symbols_long(Workspace W) {
     uint16_t* ls = W.lit_syms + mb.start + g.lit_idx;
     for (uint32_t off = k * LONG_INS + threadIdx.x; off < min(g.insert_len, (k + 1) * LONG_INS); off += 256) {
       const uint32_t pos = g.pos + off;
-      const uint8_t p1 = (W.P.abs_base || pos >= 1) ? d[(int64_t)pos - 1] : 0, p2 = (W.P.abs_base || pos >= 2) ? d[(int64_t)pos - 2] : 0;
+      const uint8_t p1 = ((uint64_t)W.P.abs_base + pos >= 1) ? d[(int64_t)pos - 1] : 0, p2 = ((uint64_t)W.P.abs_base + pos >= 2) ? d[(int64_t)pos - 2] : 0;
       const uint32_t cx = id ? ctxmap_lookup(id, context_utf8(p1, p2)) : 0u;
       ls[off] = (uint16_t)(d[pos] | (cx << 8));
     }
@@ -1472,7 +1472,7 @@ __global__ void __launch_bounds__(256) k_symbols(Workspace W) {
     W.mb[m].has_long = 1;
     return;
   }
-  uint8_t p1 = (W.P.abs_base || c.pos >= 1) ? d[(int64_t)c.pos - 1] : 0, p2 = (W.P.abs_base || c.pos >= 2) ? d[(int64_t)c.pos - 2] : 0;
+  uint8_t p1 = ((uint64_t)W.P.abs_base + c.pos >= 1) ? d[(int64_t)c.pos - 1] : 0, p2 = ((uint64_t)W.P.abs_base + c.pos >= 2) ? d[(int64_t)c.pos - 2] : 0;
   for (uint32_t j = 0; j < c.insert_len; ++j) {
     uint8_t lit = d[c.pos + j];
     uint32_t cx = id ? ctxmap_lookup(id, context_utf8(p1, p2)) : 0u;

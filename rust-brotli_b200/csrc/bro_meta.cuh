@@ -223,7 +223,7 @@ BRO_HD void emit_one_literal(W& w, const MetaCodes& mc, uint32_t rank, const uin
   }
   uint32_t tree = mc.lit.types[b] * mc.nctx;
   if (mc.ctx_map_id) {
-    uint8_t p1 = (abs_base || pos >= 1) ? data[(int64_t)pos - 1] : 0, p2 = (abs_base || pos >= 2) ? data[(int64_t)pos - 2] : 0;
+    uint8_t p1 = ((uint64_t)abs_base + pos >= 1) ? data[(int64_t)pos - 1] : 0, p2 = ((uint64_t)abs_base + pos >= 2) ? data[(int64_t)pos - 2] : 0;
     tree += ctxmap_lookup(mc.ctx_map_id, context_utf8(p1, p2));
   }
   const uint8_t lit = data[pos];
@@ -267,7 +267,7 @@ BRO_HD_NOINLINE void emit_command(W& w, const MetaCodes& mc, const Cmd& c, uint3
       if (b > 0 && mc.lit.starts[b] == lit_idx) put_block_switch(w, mc.lit, *mc.lit_sc, b, false);
     }
     uint32_t tbase = mc.lit.types[b] * mc.nctx;
-    uint8_t p1 = (abs_base || pos >= 1) ? data[(int64_t)pos - 1] : 0, p2 = (abs_base || pos >= 2) ? data[(int64_t)pos - 2] : 0;
+    uint8_t p1 = ((uint64_t)abs_base + pos >= 1) ? data[(int64_t)pos - 1] : 0, p2 = ((uint64_t)abs_base + pos >= 2) ? data[(int64_t)pos - 2] : 0;
     for (uint32_t j = 0; j < c.insert_len; ++j) {
       if (lit_idx + j == bend) {
         ++b;

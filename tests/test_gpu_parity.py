@@ -218,6 +218,17 @@ def test_compress_multi_tiny_inputs():
         assert sys_decompress(c, max(len(d), 1)) == d
 
 
+def test_ranges_starting_at_stream_offsets_1_2_3(encoder, model):
+    """A range that starts 1 or 2 bytes into the stream has fewer than two context bytes in front of its first literal:
+    the missing ones are 0, as the decoder assumes (a guard written as `abs_base || pos >= 2` read data[-1] here)."""
+    d = golden_bytes("alice29.txt")[:70000]
+    for start in (1, 2, 3):
+        head = encoder.compress_range(d, 0, start, 5, 22, True, False, True)
+        tail = encoder.compress_range(d, start, len(d) - start, 5, 22, False, True, False)
+        assert sys_decompress(head + tail, len(d)) == d
+        assert tail == model.compress_range(d, start, len(d) - start, 5, 22, False, True, False)[0]
+
+
 def test_device_resident_io(encoder):
     """Device pointers in, device pointers out (the `value` path of bench.py)."""
     import torch
