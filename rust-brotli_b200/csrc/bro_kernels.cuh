@@ -1705,7 +1705,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split_greedy(Workspace W) {
 // header sections that depend only on the block splits are serialised by extra blocks of k_trees, concurrently with
 // the prefix codes: 0..2 block-split codes (literal, command, distance), 3 literal context map, 4 distance context map
 #define HDR_SECTIONS 5
-#define SECT_BYTES 16384
+#define SECT_BYTES 32768  // worst case: 8192 context-map symbols of <= 21 bits + their prefix code
 
 // Warp-cooperative huff_create_tree(): the (count asc, symbol desc) order is a total order, so any correct sort gives
 // the reference's node order -- here a bitonic sort of 64-bit keys in shared memory by all 32 lanes; the two-queue
