@@ -30,8 +30,8 @@ ALG_BYTES_PER_POS_MATCH = 9  # 1 B input + 4 B sorted position read +
 CHUNK_BYTES = 24 << 20       # one k_match launch per chunk (csrc/bro_parse.cuh BRO_CHUNK_BYTES)
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_match launch (24 MiB chunk + 4 MiB halo) from the ncu --set full
 # capture summarised in profiles/ (None until a capture of the current kernel exists)
-NCU_MATCH_DRAM_BYTES_PER_LAUNCH = 924_980_480 + 696_341_760
-NCU_MATCH_SOURCE = "profiles/r01n_ncu_full_match_parse_scatter.txt (ncu --set full, one k_match launch: 29.4 M sorted entries)"
+NCU_MATCH_DRAM_BYTES_PER_LAUNCH = 925_193_472 + 697_299_712
+NCU_MATCH_SOURCE = "profiles/r01t_ncu_full.txt (ncu --set full, one k_match launch: 29.4 M sorted entries)"
 
 
 def load_peaks():
