@@ -109,6 +109,7 @@ struct B200Encoder {
   uint32_t unit = 4096, mb_units = 1024, lcap = 64;
   int use_rle_opt = 1, split = 1, ctx_model = 1, use_dict = 1;
   int num_lanes = 4;
+  int pair_parse = 1;     // two parse units per warp for q5 / q6 (0: one unit per warp, kept for A/B measurements)
   int shallow_match = 1;  // branch-free candidate scan for depth 16 / 32 (0: loop version, kept for A/B measurements)
   Lane lanes[kMaxLanes];
   cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams
@@ -406,7 +407,10 @@ struct B200Encoder {
       launches += 1;
     }
     mark(L, B200_ST_PARSE);
-    k_parse<<<(W.num_units + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, stream>>>(W);
+    if (pair_parse && P.n_last == 4 && P.hash_type != 9)  // two units per warp (q5, q6)
+      k_parse_pair<<<(W.num_units + 2 * PARSE_WARPS - 1) / (2 * PARSE_WARPS), PARSE_WARPS * 32, 0, stream>>>(W);
+    else
+      k_parse<<<(W.num_units + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, stream>>>(W);
     mark(L, B200_ST_FINALIZE);
     k_fin_count<<<W.num_mb, 1024, 0, stream>>>(W);
     k_fin_write<<<(W.num_units + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, stream>>>(W);
@@ -488,6 +492,7 @@ int b200_encoder_set_option(B200Encoder* e, int option, uint32_t value) {
     case B200_OPT_TIMING: e->timing = value != 0; return 1;
     case B200_OPT_DICT: e->use_dict = (int)value; return 1;
     case B200_OPT_SHALLOW_MATCH: e->shallow_match = (int)value; return 1;
+    case B200_OPT_PAIR_PARSE: e->pair_parse = (int)value; return 1;
     case B200_OPT_LANES: e->num_lanes = value < 1 ? 1 : (value > (uint32_t)kMaxLanes ? kMaxLanes : (int)value); return 1;
   }
   return 0;

@@ -1086,6 +1086,171 @@ __device__ __forceinline__ uint32_t parse_unit_warp4(const EncParams& P, const u
   return ncmd;
 }
 
+// Two parse units per warp (q5 / q6 path): each half-warp resolves a window of 4 positions x 4 cached distances, and the
+// greedy / lazy walk is written as straight-line predicated code so that the two halves never diverge.  Every "scalar"
+// of parse_unit_warp4 is a per-half value here, held redundantly by the 16 lanes of the half.  tools/window_emul.cpp
+// checks on the CPU that this windowed formulation with G = 4 reproduces parse_range() command for command; it needs
+// only ~5 % more windows than G = 8, so a warp retires almost twice the units per instruction.
+__global__ void __launch_bounds__(PARSE_WARPS * 32, 10) k_parse_pair(Workspace W) {
+  constexpr int G = 4;
+  constexpr uint32_t CAPA = 8;
+  const uint32_t FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t hbase = lane & 16u, hl = lane & 15u;
+  const uint32_t j_lane = (lane >> 2) & 3u, i_lane = lane & 3u;
+  const bool il1 = (lane & 1u) != 0, il2 = (lane & 2u) != 0;
+  const uint32_t gw = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);
+  const uint32_t u = 2u * gw + (lane >> 4);
+  const EncParams& P = W.P;
+  const uint8_t* data = W.data;
+  const uint32_t* best = W.best;
+  const bool unit_ok = u < W.num_units;
+  const uint32_t s = unit_ok ? u * P.unit : 0u, e = unit_ok ? bmin(P.n, s + P.unit) : 0u;
+  uint32_t* const out_w = reinterpret_cast<uint32_t*>(W.raw + (size_t)(unit_ok ? u : 0u) * (P.unit / 2 + 1));
+  const uint32_t htl = P.hash_type == 6 ? 8u : 4u;
+  const uint32_t window = 64u;
+  const bool D = P.use_dict != 0;
+  const bool near_start = P.abs_base < P.max_backward;
+  const bool warm = unit_ok && (u % P.mb_units) != 0 && s >= BRO_WARMUP_BYTES;
+  int stage = unit_ok ? (warm ? 0 : 1) : 2;  // 0 warm-up in front of the unit, 1 the unit, 2 done
+  uint32_t pos = stage == 0 ? s - BRO_WARMUP_BYTES : s, uend = stage == 0 ? s : e;
+  uint32_t insert_len = 0, ncmd = 0, copied = 0, arh = pos + window;
+  bool have_m = false;
+  uint32_t m_len = 0, m_dist = 0, m_score = 0;
+  int delayed = 0;
+  int32_t dc0 = 0x3fffffff, dc1 = 0x3fffffff, dc2 = 0x3fffffff, dc3 = 0x3fffffff;
+  uint32_t tail_out = 0, ncopy_out = 0, ncmd_out = 0;
+  auto advance = [&]() {  // leaves a finished stage (predicated per half)
+    if (stage < 2 && !(have_m || pos + htl < uend)) {
+      if (stage == 1) { tail_out = insert_len + (uend - pos); ncopy_out = copied; ncmd_out = ncmd; stage = 2; }
+      else { stage = 1; pos = s; uend = e; insert_len = 0; ncmd = 0; copied = 0; arh = s + window; }
+    }
+  };
+  advance();
+  advance();
+  while (__any_sync(FULL, stage < 2)) {
+    const bool act = stage < 2;
+    // ---------------- phase A: the 4 positions of this half's window, 4 cache candidates each ----------------
+    const uint32_t wbase = pos;
+    const uint32_t p = wbase + j_lane;
+    const bool p_ok = act && p < uend;
+    const uint32_t maxl = p_ok ? uend - p : 0u;
+    uint32_t clen = 0, cdist = 0, key = 0;
+    if (p_ok) {
+      const int32_t back = il2 ? (il1 ? dc3 : dc2) : (il1 ? dc1 : dc0);
+      const uint32_t mb = near_start ? bmin(p + P.abs_base, P.max_backward) : P.max_backward;
+      if (back > 0 && (uint32_t)back <= mb) {
+        const uint64_t x = ldu64(data + p) ^ ldu64(data + p - back);
+        uint32_t len = x ? ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : CAPA;
+        len = bmin(len, maxl);
+        if (len == CAPA && maxl > CAPA) len = lane_lcp_ext(data + p, (uint32_t)back, CAPA, maxl);
+        if (len >= 3 || (len == 2 && i_lane < 2)) {
+          const uint32_t score = score_last_distance(5, len, i_lane);
+          key = (score << 2) | (3u - i_lane);
+          clen = len;
+          cdist = (uint32_t)back;
+        }
+      }
+    }
+    {
+      uint32_t k = key;
+      k = max(k, __shfl_xor_sync(FULL, k, 1));
+      k = max(k, __shfl_xor_sync(FULL, k, 2));
+      const int src = (int)((lane & ~3u) + (3u - (k & 3u)));
+      const uint32_t wl = __shfl_sync(FULL, clen, src), wd = __shfl_sync(FULL, cdist, src);
+      key = k; clen = wl; cdist = wd;
+    }
+    uint32_t f_score = key ? (key >> 2) : BRO_MIN_SCORE, f_len = key ? clen : 0u, f_dist = key ? cdist : 0u;
+    bool f_found = key != 0;
+    if (p_ok && i_lane == 0) {
+      const uint32_t b = best[p];
+      const uint32_t blen = b & 0xFFu;
+      if (b & BRO_BEST_DICT) {
+        Match dm;
+        const uint32_t mb = near_start ? bmin(p + P.abs_base, P.max_backward) : P.max_backward;
+        if (!f_found && D && dict_decode(b, 5, maxl, mb, &dm)) { f_found = true; f_len = dm.len; f_dist = dm.dist; f_score = dm.score; }
+      } else if (blen != 0) {
+        const uint32_t bdist = b >> 8;
+        uint32_t len = bmin(blen, maxl);
+        if (blen >= P.lcap && maxl > len) len = lane_lcp_ext(data + p, bdist, len, maxl);
+        if (len >= 4) {
+          const uint32_t score = score_regular(5, len, bdist);
+          if (f_score < score) { f_score = score; f_len = len; f_dist = bdist; f_found = true; }
+        }
+      }
+    }
+    uint32_t found = (__ballot_sync(FULL, f_found && i_lane == 0) >> hbase) & 0xFFFFu;  // bits 0,4,8,12 of this half
+    found = (found | (found >> 3) | (found >> 6) | (found >> 9)) & 0xFu;              // bit j <=> a match exists at wbase + j
+
+    // ---------------- phase B: the walk of parse_unit_warp4 as straight-line predicated code ----------------
+    bool wdone = !act, accept = false;
+    uint32_t j = 0;
+    {
+      const bool doA = act && !have_m;
+      const uint32_t lim = doA ? bmin((uint32_t)G, uend - htl - wbase) : 0u;
+      const uint32_t cand = found & ((1u << lim) - 1u);
+      const uint32_t f = cand ? (uint32_t)(__ffs((int)cand) - 1) : lim;
+      uint32_t steps = f;
+      bool jump = false;
+      if (f > 0 && pos + f > arh) { steps = pos > arh ? 1u : (arh - pos + 1u); jump = true; }
+      if (doA) { insert_len += steps; pos += steps; j = steps; }
+      const int src = (int)(hbase + 4u * bmin(j, (uint32_t)G - 1u));
+      const uint32_t a_len = __shfl_sync(FULL, f_len, src), a_dist = __shfl_sync(FULL, f_dist, src), a_score = __shfl_sync(FULL, f_score, src);
+      if (doA && jump) {
+        const uint32_t margin = bmax(htl - 1u, 4u);
+        if (pos + 16 + margin >= uend) { insert_len += uend - pos; pos = uend; }
+        else if (pos > arh + 4 * window) { insert_len += 16; pos += 16; }
+        else { insert_len += 8; pos += 8; }
+        wdone = true;
+      } else if (doA && (!cand || j >= (uint32_t)G)) {
+        wdone = true;
+      } else if (doA) {
+        m_len = a_len; m_dist = a_dist; m_score = a_score;
+        have_m = true;
+        delayed = 0;
+      }
+    }
+#pragma unroll
+    for (int st = 0; st < G - 1; ++st) {
+      const bool doB = !wdone && !accept && have_m;
+      const int src = (int)(hbase + 4u * bmin(j + 1u, (uint32_t)G - 1u));
+      const uint32_t b_len = __shfl_sync(FULL, f_len, src), b_dist = __shfl_sync(FULL, f_dist, src), b_score = __shfl_sync(FULL, f_score, src);
+      if (doB && j + 1u >= (uint32_t)G) {
+        wdone = true;  // re-probe with the window starting at pos
+      } else if (doB) {
+        const bool f2 = (found >> (j + 1u)) & 1u;
+        if (f2 && b_score >= m_score + 175u) {
+          pos++;
+          insert_len++;
+          j++;
+          m_len = b_len; m_dist = b_dist; m_score = b_score;
+          if (!(++delayed < 4 && pos + htl < uend)) accept = true;
+        } else {
+          accept = true;
+        }
+      }
+    }
+    if (accept) {
+      const uint32_t m_bytes = len_bytes(m_len);
+      arh = pos + 2 * m_bytes + window;
+      if (!len_is_dict(m_len) && (int32_t)m_dist != dc0) { dc3 = dc2; dc2 = dc1; dc1 = dc0; dc0 = (int32_t)m_dist; }
+      if (stage == 1 && hl < 3) out_w[3u * ncmd + hl] = hl == 0 ? insert_len : (hl == 1 ? m_len : m_dist);
+      ++ncmd;
+      insert_len = 0;
+      copied += m_bytes;
+      pos += m_bytes;
+      have_m = false;
+    }
+    advance();
+    advance();
+  }
+  if (unit_ok && hl == 0) {
+    W.unit_ncmd[u] = ncmd_out;
+    W.unit_tail[u] = tail_out;
+    W.unit_ncopy[u] = ncopy_out;
+  }
+}
+
 #ifndef PARSE_MIN_BLOCKS
 #define PARSE_MIN_BLOCKS 10
 #endif
