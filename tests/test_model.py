@@ -2,6 +2,7 @@
 kernels).  It must produce valid brotli, stay within +0.5 % of the reference restatement, and match its goldens --
 the GPU tests then assert that the kernels reproduce these streams bit for bit."""
 import hashlib
+import os
 
 import pytest
 
@@ -56,3 +57,33 @@ def test_model_options(model):
         c, _ = model.compress(d, 5, 22, **kw)
         assert sys_decompress(c, len(d)) == d
         assert len(c) < len(base) * 1.03
+
+
+def test_windowed_parse_formulation_equals_sequential_spec(model):
+    """The parse kernels resolve a window of G positions with the distance cache of the window start and then walk it with
+    straight-line predicated code (G = 8: one unit per warp, G = 4: two units per warp).  tools/window_emul.cpp is that
+    formulation on the CPU; it must reproduce parse_range() command for command, for both window sizes."""
+    import ctypes
+    import subprocess
+    import numpy as np
+    from conftest import golden_bytes
+    from tools.model_harness import EncParams
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(root, "tools", "libwindow_emul.so")
+    src = os.path.join(root, "tools", "window_emul.cpp")
+    if not os.path.exists(so) or os.path.getmtime(src) > os.path.getmtime(so):
+        subprocess.check_call(["g++", "-O2", "-fwrapv", "-std=c++17", "-shared", "-fPIC", "-w", "-I",
+                               os.path.join(root, "rust-brotli_b200", "csrc"), src, "-o", so])
+    L = ctypes.CDLL(so)
+    L.window_emul_check.argtypes = [ctypes.POINTER(EncParams), ctypes.c_char_p, ctypes.c_void_p, ctypes.c_uint32,
+                                    ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+    for name in ("alice29.txt", "random_then_unicode", "compressed_file", "quickfox_repeated"):
+        d = golden_bytes(name)
+        for q in (5, 6):
+            p = model.params(q, 22, len(d), len(d))
+            best = np.zeros(len(d) + 1, dtype=np.uint32)
+            model.compress(d, q, 22, best_out=best.ctypes.data)
+            w4, w8 = ctypes.c_uint64(0), ctypes.c_uint64(0)
+            bad = L.window_emul_check(ctypes.byref(p), d + bytes(512), best.ctypes.data, len(d), ctypes.byref(w4), ctypes.byref(w8))
+            assert bad == 0, (name, q)
+            assert w4.value <= w8.value * 1.25  # G = 4 costs few extra windows
