@@ -109,7 +109,7 @@ struct B200Encoder {
   uint32_t unit = 4096, mb_units = 1024, lcap = 64;
   int use_rle_opt = 1, split = 1, ctx_model = 1, use_dict = 1;
   int num_lanes = 4;
-  int pair_parse = 1;     // two parse units per warp for q5 / q6 (0: one unit per warp, kept for A/B measurements)
+  int pair_parse = 2;     // parse units per warp for q5 / q6: 2 or 4 (0: one unit per warp; kept for A/B measurements)
   int shallow_match = 1;  // branch-free candidate scan for depth 16 / 32 (0: loop version, kept for A/B measurements)
   Lane lanes[kMaxLanes];
   cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams
@@ -407,8 +407,10 @@ struct B200Encoder {
       launches += 1;
     }
     mark(L, B200_ST_PARSE);
-    if (pair_parse && P.n_last == 4 && P.hash_type != 9)  // two units per warp (q5, q6)
-      k_parse_pair<<<(W.num_units + 2 * PARSE_WARPS - 1) / (2 * PARSE_WARPS), PARSE_WARPS * 32, 0, stream>>>(W);
+    if (pair_parse == 4 && P.n_last == 4 && P.hash_type != 9)  // four units per warp (q5, q6)
+      k_parse_pair<4><<<(W.num_units + 4 * PARSE_WARPS - 1) / (4 * PARSE_WARPS), PARSE_WARPS * 32, 0, stream>>>(W);
+    else if (pair_parse && P.n_last == 4 && P.hash_type != 9)  // two units per warp
+      k_parse_pair<2><<<(W.num_units + 2 * PARSE_WARPS - 1) / (2 * PARSE_WARPS), PARSE_WARPS * 32, 0, stream>>>(W);
     else
       k_parse<<<(W.num_units + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, stream>>>(W);
     mark(L, B200_ST_FINALIZE);

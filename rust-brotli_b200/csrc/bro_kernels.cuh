@@ -1091,16 +1091,20 @@ __device__ __forceinline__ uint32_t parse_unit_warp4(const EncParams& P, const u
 // of parse_unit_warp4 is a per-half value here, held redundantly by the 16 lanes of the half.  tools/window_emul.cpp
 // checks on the CPU that this windowed formulation with G = 4 reproduces parse_range() command for command; it needs
 // only ~5 % more windows than G = 8, so a warp retires almost twice the units per instruction.
+// UPW = units per warp: 2 (half-warps, windows of 4 positions) or 4 (quarter-warps, windows of 2 positions; the emulation
+// counts 1.3x the windows of UPW = 2, each of them cheaper: one lazy step instead of three).
+template <int UPW>
 __global__ void __launch_bounds__(PARSE_WARPS * 32, 10) k_parse_pair(Workspace W) {
-  constexpr int G = 4;
+  constexpr int G = 8 / UPW;
+  constexpr uint32_t SUB = 32 / UPW;  // lanes per unit
   constexpr uint32_t CAPA = 8;
   const uint32_t FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t hbase = lane & 16u, hl = lane & 15u;
-  const uint32_t j_lane = (lane >> 2) & 3u, i_lane = lane & 3u;
+  const uint32_t hbase = lane & ~(SUB - 1u), hl = lane & (SUB - 1u);
+  const uint32_t j_lane = hl >> 2, i_lane = lane & 3u;
   const bool il1 = (lane & 1u) != 0, il2 = (lane & 2u) != 0;
   const uint32_t gw = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);
-  const uint32_t u = 2u * gw + (lane >> 4);
+  const uint32_t u = (uint32_t)UPW * gw + lane / SUB;
   const EncParams& P = W.P;
   const uint8_t* data = W.data;
   const uint32_t* best = W.best;
@@ -1179,8 +1183,10 @@ __global__ void __launch_bounds__(PARSE_WARPS * 32, 10) k_parse_pair(Workspace W
         }
       }
     }
-    uint32_t found = (__ballot_sync(FULL, f_found && i_lane == 0) >> hbase) & 0xFFFFu;  // bits 0,4,8,12 of this half
-    found = (found | (found >> 3) | (found >> 6) | (found >> 9)) & 0xFu;              // bit j <=> a match exists at wbase + j
+    const uint32_t bal = __ballot_sync(FULL, f_found && i_lane == 0) >> hbase;  // bits 0, 4, .. of this unit's lanes
+    uint32_t found = 0;                                                         // bit j <=> a match exists at wbase + j
+#pragma unroll
+    for (int jj = 0; jj < G; ++jj) found |= ((bal >> (4 * jj)) & 1u) << jj;
 
     // ---------------- phase B: the walk of parse_unit_warp4 as straight-line predicated code ----------------
     bool wdone = !act, accept = false;
