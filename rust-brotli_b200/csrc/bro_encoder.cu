@@ -109,7 +109,7 @@ struct B200Encoder {
   uint32_t unit = 4096, mb_units = 1024, lcap = 64;
   int use_rle_opt = 1, split = 1, ctx_model = 1, use_dict = 1;
   int num_lanes = 4;
-  int pair_parse = 2;     // parse units per warp for q5 / q6: 2 or 4 (0: one unit per warp; kept for A/B measurements)
+  int pair_parse = 4;     // parse units per warp for q5 / q6: 4 (default) or 2; 0 = one unit per warp (kept for A/B measurements)
   int shallow_match = 1;  // branch-free candidate scan for depth 16 / 32 (0: loop version, kept for A/B measurements)
   Lane lanes[kMaxLanes];
   cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams
