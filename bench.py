@@ -304,7 +304,7 @@ def main():
         stage_ms = {k: round(v / args.steps, 3) for k, v in stage_acc.items()}
         achieved = (ALG_BYTES_PER_POS_MATCH * NB) / (match_ms * 1e-3) / 1e9 if match_ms > 0 else None
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is timed at N = 1 only
             sample = shard[:16_000_000]
             mbps, _ = cpu_port_throughput(sample, 1)
             cpu = {"value": round(mbps, 2), "unit": "MB/s", "cores": 1, "kind": "port",
