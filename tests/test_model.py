@@ -79,7 +79,7 @@ def test_windowed_parse_formulation_equals_sequential_spec(model):
                                     ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
     for name in ("alice29.txt", "random_then_unicode", "compressed_file", "quickfox_repeated"):
         d = golden_bytes(name)
-        for q in (5, 6):
+        for q in (5, 6, 7, 9):  # q7 / q9: 10 / 16 cache candidates, the H9 scores, the 512-byte literal-spree window
             p = model.params(q, 22, len(d), len(d))
             best = np.zeros(len(d) + 1, dtype=np.uint32)
             model.compress(d, q, 22, best_out=best.ctypes.data)
