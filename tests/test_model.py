@@ -87,3 +87,37 @@ def test_windowed_parse_formulation_equals_sequential_spec(model):
             bad = L.window_emul_check(ctypes.byref(p), d + bytes(512), best.ctypes.data, len(d), ctypes.byref(w4), ctypes.byref(w8))
             assert bad == 0, (name, q)
             assert w4.value <= w8.value * 1.25  # G = 4 costs few extra windows
+
+
+def test_model_two_chunks_roundtrip(model):
+    """Streams longer than one 24 MiB chunk: the chunk loop (shared with the device encoder) appends independent chunks to one
+    bit stream; matches may reach back across the seam (left halo), nothing may read across it to the right."""
+    from tools import datagen
+    d = datagen.enwik_like(26_000_000, seed=11)
+    c, st = model.compress(d, 5, 22)
+    assert st.num_metablocks == 7  # 6 in the first chunk, 1 in the second
+    assert sys_decompress(c, len(d)) == d
+    assert len(c) < 0.36 * len(d)
+
+
+def test_model_structured_logs_within_half_percent_of_reference_restatement(model, oracle):
+    """The 256-byte warm-up in front of every parse unit keeps record-structured input at reference size
+    (+1.4 % without it)."""
+    from tools import datagen
+    d = datagen.json_logs(4_000_000)
+    for q in (5, 9):
+        c = model.compress(d, q, 22)[0]
+        assert sys_decompress(c, len(d)) == d
+        assert len(c) <= len(oracle.compress(d, q, 22)[0]) * 1.005
+
+
+def test_model_static_dictionary_reaches_libbrotlienc_on_english(model):
+    """Config 1 (alice29, q5, lgwin 20): with static-dictionary matches the size is within 0.5 % of Google's encoder, whose
+    code the reference is a port of (52 809 B); without them it is 0.7 % larger."""
+    from oracle.harness import sys_compress
+    d = golden_bytes("alice29.txt")
+    on = model.compress(d, 5, 20)[0]
+    off = model.compress(d, 5, 20, use_dict=0)[0]
+    ref = len(sys_compress(d, 5, 20))
+    assert sys_decompress(on, len(d)) == d and sys_decompress(off, len(d)) == d
+    assert len(on) <= ref * 1.005 < len(off)
