@@ -77,7 +77,11 @@ typedef struct BrotliEncoderWorkPoolStruct BrotliEncoderWorkPool;
 /* ---- single stream: src/ffi/compressor.rs ---- */
 /* :72  BrotliEncoderCreateInstance.  Host-side bookkeeping uses alloc_func when given; device memory is owned by the state. */
 BrotliEncoderState* BrotliEncoderCreateInstance(brotli_alloc_func alloc_func, brotli_free_func free_func, void* opaque);
-/* :115 BrotliEncoderSetParameter (refused after the first byte was consumed, encode.rs:289-295) */
+/* :115 BrotliEncoderSetParameter (refused after the first byte was consumed, encode.rs:289-295).  Also refused
+ * (BROTLI_FALSE, state unchanged): a value this path cannot honour -- LARGE_WINDOW != 0 and the framing parameters
+ * (CATABLE, APPENDABLE, MAGIC_NUMBER, BYTE_ALIGN, BARE_STREAM) unless INTEGRATION.md lists the mode as produced.
+ * QUALITY: 5..9 run the hash-chain family, 10 and 11 the optimal-parse family; values below 5 run as 5 (the q0..q4
+ * hashers are not built) -- b200_effective_quality() reports the quality that will really be used. */
 BROTLI_BOOL BrotliEncoderSetParameter(BrotliEncoderState* state, BrotliEncoderParameter p, uint32_t value);
 /* :128 */
 void BrotliEncoderDestroyInstance(BrotliEncoderState* state);
@@ -90,6 +94,17 @@ BROTLI_BOOL BrotliEncoderCompress(int quality, int lgwin, BrotliEncoderMode mode
 /* :280 BrotliEncoderCompressStream */
 BROTLI_BOOL BrotliEncoderCompressStream(BrotliEncoderState* state, BrotliEncoderOperation op, size_t* available_in,
                                         const uint8_t** next_in, size_t* available_out, uint8_t** next_out, size_t* total_out);
+/* :260 BrotliEncoderCompressStreaming -- CompressStream with the buffer pointers passed by value and no total_out */
+BROTLI_BOOL BrotliEncoderCompressStreaming(BrotliEncoderState* state, BrotliEncoderOperation op, size_t* available_in,
+                                           const uint8_t* input_buf, size_t* available_out, uint8_t* output_buf);
+/* :162 BrotliEncoderSetCustomDictionary -- the last min(size, 2^lgwin - 16) bytes of dict become window content in front
+ * of the stream; the static dictionary is switched off (encode.rs:1205-1260).  Must precede the first input byte. */
+void BrotliEncoderSetCustomDictionary(BrotliEncoderState* state, size_t size, const uint8_t* dict);
+/* :359-419 host memory through the instance's allocator (malloc / free when none was given) */
+uint8_t* BrotliEncoderMallocU8(BrotliEncoderState* state, size_t size);
+void BrotliEncoderFreeU8(BrotliEncoderState* state, uint8_t* data, size_t size);
+size_t* BrotliEncoderMallocUsize(BrotliEncoderState* state, size_t size);
+void BrotliEncoderFreeUsize(BrotliEncoderState* state, size_t* data, size_t size);
 /* :150-192 */
 BROTLI_BOOL BrotliEncoderIsFinished(BrotliEncoderState* state);
 BROTLI_BOOL BrotliEncoderHasMoreOutput(BrotliEncoderState* state);
@@ -118,6 +133,7 @@ int32_t BrotliEncoderCompressWorkPool(BrotliEncoderWorkPool* work_pool, size_t n
 /* ---- device-resident entry points (B200 additions; pointers are CUDA device pointers where noted) ---- */
 typedef struct B200Encoder B200Encoder;
 int b200_device_count(void);
+int b200_effective_quality(int requested_quality);
 B200Encoder* b200_encoder_create(int device);
 void b200_encoder_destroy(B200Encoder* e);
 int b200_encoder_set_option(B200Encoder* e, int option, uint32_t value);

@@ -223,6 +223,8 @@ typedef struct {
   uint64_t hash_mask;
   uint16_t* num;
   uint32_t* buckets;
+  int use_dictionary;                            /* params.use_dictionary (encode.rs:559-562: off for catable) */
+  size_t dict_num_lookups, dict_num_matches;     /* Struct1 of the hasher (mod.rs:161-169) */
 } Hasher;
 
 typedef struct {
@@ -295,6 +297,55 @@ static void PrepareDistanceCache(int* dc, int num) {
   }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Static dictionary: SearchInStaticDictionary / TestStaticDictionaryItem, mod.rs:1890-1988.  The dictionary bytes and
+ * kStaticDictionaryHash come from the system's brotli libraries at build time (oracle/gen_dict_data.py).
+ * ---------------------------------------------------------------------------------------------- */
+#include "dict_data.inc"
+#define kCutoffTransformsCount 10u
+#define kCutoffTransforms 0x071B520ADA2D3200ull
+#define kMaxDistance 0x3fffffcu /* params.dist.max_distance, large_window off (encode.rs:318-325) */
+static inline uint32_t Hash14(const uint8_t* p) {
+  uint32_t v;
+  memcpy(&v, p, 4);
+  return (v * kHashMul32) >> (32 - 14);
+}
+static int TestStaticDictionaryItem(size_t item, const uint8_t* data, size_t max_length, size_t max_backward, int h9,
+                                    SearchResult* out) { /* mod.rs:1895-1938 */
+  size_t len = item & 0x1f, dist = item >> 5;
+  size_t offset = kDictOffsets[len] + len * dist;
+  if (len > max_length) return 0;
+  size_t matchlen = FindMatchLengthWithLimit(data, kBrotliDictionaryData + offset, len);
+  if (matchlen + kCutoffTransformsCount <= len || matchlen == 0) return 0;
+  uint64_t cut = len - matchlen;
+  size_t transform_id = (size_t)((cut << 2) + ((kCutoffTransforms >> (cut * 6)) & 0x3f));
+  size_t backward = max_backward + dist + 1 + (transform_id << kDictSizeBits[len]);
+  if (backward > kMaxDistance) return 0;
+  uint64_t score = h9 ? ((1920ull * 4 + 540ull * matchlen - 120ull * Log2FloorNonZero(backward)) >> 2)
+                      : Score(matchlen, backward);
+  if (score < out->score) return 0;
+  out->len = matchlen;
+  out->len_x_code = len ^ matchlen;
+  out->distance = backward;
+  out->score = score;
+  return 1;
+}
+static int SearchInStaticDictionary(Hasher* h, const uint8_t* data, size_t max_length, size_t max_backward,
+                                    SearchResult* out) { /* mod.rs:1940-1988, shallow = false */
+  int found = 0;
+  if (h->dict_num_matches < (h->dict_num_lookups >> 7)) return 0;
+  size_t key = (size_t)Hash14(data) << 1;
+  for (int i = 0; i < 2; ++i, ++key) {
+    size_t item = kStaticDictionaryHash[key];
+    h->dict_num_lookups++;
+    if (item != 0 && TestStaticDictionaryItem(item, data, max_length, max_backward, h->type == 9, out)) {
+      h->dict_num_matches++;
+      found = 1;
+    }
+  }
+  return found;
+}
+
 /* AdvHasher::FindLongestMatch, mod.rs:1684-1812 (ring mask dropped: the oracle works on a flat buffer). */
 static int FindLongestMatchAdv(Hasher* h, const uint8_t* data, const int* dist_cache, size_t cur_ix,
                                size_t max_length, size_t max_backward, SearchResult* out) {
@@ -350,6 +401,7 @@ static int FindLongestMatchAdv(Hasher* h, const uint8_t* data, const int* dist_c
   }
   bucket[num_copy & h->block_mask] = (uint32_t)cur_ix;
   h->num[key] = (uint16_t)(num_copy + 1);
+  if (!found && h->use_dictionary) found = SearchInStaticDictionary(h, cur, max_length, max_backward, out); /* :1797-1810 */
   return found;
 }
 
@@ -412,6 +464,7 @@ static int FindLongestMatchH9(Hasher* h, const uint8_t* data, const int* dist_ca
     bucket[num_copy & h->block_mask] = (uint32_t)cur_ix;
     h->num[key] = (uint16_t)(num_copy + 1);
   }
+  if (!found && h->use_dictionary) found = SearchInStaticDictionary(h, cur, max_length, max_backward, out); /* :862-875 */
   return found;
 }
 
@@ -1563,6 +1616,7 @@ static int ShouldCompress(const uint8_t* data, size_t last_flush_pos, size_t byt
 
 /* flags */
 #define ORACLE_FLAG_NO_CONTEXT_MODELING 1
+#define ORACLE_FLAG_NO_DICTIONARY 2
 
 size_t oracle_brotli_compress(int quality, int lgwin, const uint8_t* input_in, size_t input_size, uint8_t* out,
                               size_t out_cap, size_t size_hint, int flags, OracleStats* stats) {
@@ -1586,6 +1640,7 @@ size_t oracle_brotli_compress(int quality, int lgwin, const uint8_t* input_in, s
 
   Hasher h; /* ChooseHasher encode.rs:834-893 (H40-42 are unsupported there and fall back to H6, :1096-1114) */
   memset(&h, 0, sizeof(h));
+  h.use_dictionary = !(flags & ORACLE_FLAG_NO_DICTIONARY);
   if (quality == 9) {
     h.type = 9; h.n_last = 16; h.block_bits = 8; h.bucket_bits = 15; h.hash_len = 4;
   } else if (lgwin <= 16) {

@@ -22,7 +22,7 @@ from ._native import DeviceEncoder, lib  # noqa: F401
 BROTLI_PARAM_MODE, BROTLI_PARAM_QUALITY, BROTLI_PARAM_LGWIN, BROTLI_PARAM_LGBLOCK = 0, 1, 2, 3
 BROTLI_PARAM_DISABLE_LITERAL_CONTEXT_MODELING, BROTLI_PARAM_SIZE_HINT, BROTLI_PARAM_LARGE_WINDOW = 4, 5, 6
 BROTLI_PARAM_CATABLE, BROTLI_PARAM_APPENDABLE, BROTLI_PARAM_MAGIC_NUMBER = 167, 168, 169
-BROTLI_PARAM_BYTE_ALIGN, BROTLI_PARAM_BARE_STREAM = 172, 173
+BROTLI_PARAM_NO_DICTIONARY, BROTLI_PARAM_BYTE_ALIGN, BROTLI_PARAM_BARE_STREAM = 170, 172, 173
 BROTLI_OPERATION_PROCESS, BROTLI_OPERATION_FLUSH, BROTLI_OPERATION_FINISH = 0, 1, 2
 MAX_THREADS = 16  # src/enc/fixed_queue.rs:1
 
@@ -53,6 +53,7 @@ class BrotliEncoderParams:
     magic_number: bool = False
     byte_align: bool = False
     bare_stream: bool = False
+    use_dictionary: bool = True
 
     def as_key_values(self):
         kv = [(BROTLI_PARAM_QUALITY, self.quality), (BROTLI_PARAM_LGWIN, self.lgwin), (BROTLI_PARAM_MODE, self.mode)]
@@ -60,6 +61,16 @@ class BrotliEncoderParams:
             kv.append((BROTLI_PARAM_SIZE_HINT, min(self.size_hint, 0xFFFFFFFF)))
         if self.disable_literal_context_modeling:
             kv.append((BROTLI_PARAM_DISABLE_LITERAL_CONTEXT_MODELING, 1))
+        if self.lgblock:
+            kv.append((BROTLI_PARAM_LGBLOCK, self.lgblock))
+        if not self.use_dictionary:
+            kv.append((BROTLI_PARAM_NO_DICTIONARY, 1))
+        # framing parameters are forwarded, never dropped: the C ABI refuses the ones this path cannot produce
+        for key, on in ((BROTLI_PARAM_CATABLE, self.catable), (BROTLI_PARAM_APPENDABLE, self.appendable),
+                        (BROTLI_PARAM_MAGIC_NUMBER, self.magic_number), (BROTLI_PARAM_BYTE_ALIGN, self.byte_align),
+                        (BROTLI_PARAM_BARE_STREAM, self.bare_stream)):
+            if on:
+                kv.append((key, 1))
         return kv
 
 
@@ -88,6 +99,12 @@ def _capi():
         L.BrotliEncoderCompressMulti.argtypes = [sz, vp, vp, sz, vp, ctypes.POINTER(sz), vp, sz, vp, vp, vp]
         L.BrotliEncoderCompressMulti.restype = ctypes.c_int32
         L.BrotliEncoderVersion.restype = ctypes.c_uint32
+        L.BrotliEncoderSetCustomDictionary.argtypes = [vp, sz, vp]
+        L.BrotliEncoderSetCustomDictionary.restype = None
+        L.BrotliEncoderCompressStreaming.argtypes = [vp, ctypes.c_int, ctypes.POINTER(sz), vp, ctypes.POINTER(sz), vp]
+        L.BrotliEncoderCompressStreaming.restype = ctypes.c_int
+        L.b200_effective_quality.argtypes = [ctypes.c_int]
+        L.b200_effective_quality.restype = ctypes.c_int
         L._capi_ready = True
     return L
 
@@ -121,7 +138,9 @@ class _Stream:
         if not self.h:
             raise IOError("BrotliEncoderCreateInstance failed: no usable CUDA device")
         for k, v in params.as_key_values():
-            self.L.BrotliEncoderSetParameter(self.h, k, int(v))
+            if not self.L.BrotliEncoderSetParameter(self.h, k, int(v)):
+                self.close()
+                raise ValueError("BrotliEncoderSetParameter(%d, %d) refused: not produced by this path" % (k, int(v)))
 
     def step(self, data: bytes, op: int) -> bytes:
         out = bytearray()

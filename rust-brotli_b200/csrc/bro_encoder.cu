@@ -169,8 +169,7 @@ struct B200Encoder {
 
   void fill_params(EncParams* P, int quality, int lgwin, uint64_t size_hint) const {
     memset(P, 0, sizeof(*P));
-    if (quality < 5) quality = 5;  // the device path implements the hash-chain family q5..q9
-    if (quality > 9) quality = 9;
+    quality = b200_effective_quality(quality);
     if (lgwin < 10) lgwin = 10;
     if (lgwin > 24) lgwin = 24;
     P->quality = quality;
@@ -467,6 +466,13 @@ int b200_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
   return n;
+}
+// The quality the device path runs for a requested one: 5..9 hash-chain family (encode.rs:834-893), 10 / 11 optimal parse;
+// q0..q4 (BasicHasher H2..H54, fragment compressors) are not built and run as 5.
+int b200_effective_quality(int requested_quality) {
+  if (requested_quality < 5) return 5;
+  if (requested_quality > 9) return 9;
+  return requested_quality;
 }
 
 B200Encoder* b200_encoder_create(int device) {

@@ -12,6 +12,7 @@ enum { B200_OPT_UNIT = 1, B200_OPT_MB_UNITS = 2, B200_OPT_LCAP = 3, B200_OPT_RLE
 enum { B200_ST_SORT = 0, B200_ST_MATCH = 1, B200_ST_PARSE = 2, B200_ST_FINALIZE = 3, B200_ST_SPLIT = 4, B200_ST_HEADER = 5,
        B200_ST_EMIT = 6, B200_NUM_STAGES = 7 };
 int b200_device_count(void);
+int b200_effective_quality(int requested_quality);
 B200Encoder* b200_encoder_create(int device);
 void b200_encoder_destroy(B200Encoder* e);
 int b200_encoder_set_option(B200Encoder* e, int option, uint32_t value);

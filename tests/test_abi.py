@@ -43,9 +43,20 @@ def test_pure_host_functions():
     L = ctypes.CDLL(LIB)
     L.BrotliEncoderMaxCompressedSize.restype = ctypes.c_size_t
     L.BrotliEncoderMaxCompressedSize.argtypes = [ctypes.c_size_t]
-    assert L.BrotliEncoderMaxCompressedSize(0) == 2
-    for n in (1, 1000, 1 << 20, 1 << 30):
-        assert L.BrotliEncoderMaxCompressedSize(n) > n
+    def ref(n):  # encode.rs:1277-1299 restated (64-bit wrapping arithmetic)
+        M = (1 << 64) - 1
+        blocks = n >> 14
+        tail = (n - (blocks << 24)) & M
+        res = (n + 2 + 4 * blocks + (4 if tail > (1 << 20) else 3) + 1) & M
+        return 17 if n == 0 else (0 if res < n else res + 16)
+    assert L.BrotliEncoderMaxCompressedSize(0) == 17
+    for n in (1, 1000, 16384, 1 << 20, (1 << 24) + 5, 1 << 30, 5 << 30):
+        assert L.BrotliEncoderMaxCompressedSize(n) == ref(n) > n
+    L.BrotliEncoderMaxCompressedSizeMulti.restype = ctypes.c_size_t
+    L.BrotliEncoderMaxCompressedSizeMulti.argtypes = [ctypes.c_size_t, ctypes.c_size_t]
+    assert L.BrotliEncoderMaxCompressedSizeMulti(1000, 8) == ref(1000) + 64  # encode.rs:1273-1275
+    L.b200_effective_quality.restype = ctypes.c_int
+    assert [L.b200_effective_quality(q) for q in (0, 4, 5, 9)] == [5, 5, 5, 9]
     L.BrotliEncoderVersion.restype = ctypes.c_uint32
     assert L.BrotliEncoderVersion() >> 24 == 8
 

@@ -9,7 +9,7 @@ import io
 import numpy as np
 import pytest
 
-from conftest import golden_bytes
+from conftest import assert_size_parity, golden_bytes
 from oracle.harness import sys_compress, sys_decompress
 
 pytestmark = pytest.mark.gpu

@@ -6,7 +6,7 @@ import os
 
 import pytest
 
-from conftest import golden_bytes
+from conftest import assert_size_parity, golden_bytes
 from oracle.harness import sys_decompress
 
 FILES = ["alice29.txt", "asyoulik.txt", "random_then_unicode", "quickfox_repeated", "random_org_10k.bin", "backward65536",
@@ -21,10 +21,7 @@ def test_model_golden_roundtrip_and_size(model, golden_table, name, q, w):
     assert sys_decompress(c, len(d)) == d
     g = golden_table["%s|q%d|w%d" % (name, q, w)]
     assert hashlib.sha256(c).hexdigest() == g["model_sha256"]
-    # size parity with the reference restatement: <= +0.5 % (absolute slack of 8 bytes for tiny streams)
-    # reference size = the restatement without static dictionary, or Google's encoder with it, whichever is larger (on
-    # tiny inputs dictionary references cost a few bytes: quickfox_repeated is 46 B without, 51 B with)
-    assert len(c) <= max(g["oracle_size"], g["libbrotlienc_size"]) * 1.005 + 8
+    assert_size_parity(len(c), g["oracle_size"], "%s q%d w%d" % (name, q, w))
 
 
 @pytest.mark.parametrize("shards", [1, 2, 3, 5])
@@ -66,7 +63,7 @@ def test_windowed_parse_formulation_equals_sequential_spec(model):
     import ctypes
     import subprocess
     import numpy as np
-    from conftest import golden_bytes
+    from conftest import assert_size_parity, golden_bytes
     from tools.model_harness import EncParams
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     so = os.path.join(root, "tools", "libwindow_emul.so")
