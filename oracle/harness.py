@@ -55,6 +55,36 @@ def sys_decompress(comp: bytes, max_out: int) -> bytes:
     return out.raw[:sz.value]
 
 
+def sys_decompress_with_dictionary(comp: bytes, max_out: int, dictionary: bytes) -> bytes:
+    """Streaming decode through libbrotlidec with a raw (LZ77 prefix) dictionary attached -- what a decoder of a stream
+    made after BrotliEncoderSetCustomDictionary has to do."""
+    _, dec = _libs()
+    dec.BrotliDecoderCreateInstance.restype = ctypes.c_void_p
+    dec.BrotliDecoderCreateInstance.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    dec.BrotliDecoderAttachDictionary.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_char_p]
+    dec.BrotliDecoderAttachDictionary.restype = ctypes.c_int
+    dec.BrotliDecoderDecompressStream.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_void_p),
+                                                  ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]
+    dec.BrotliDecoderDecompressStream.restype = ctypes.c_int
+    dec.BrotliDecoderDestroyInstance.argtypes = [ctypes.c_void_p]
+    st = dec.BrotliDecoderCreateInstance(None, None, None)
+    try:
+        if not dec.BrotliDecoderAttachDictionary(st, 0, len(dictionary), dictionary):  # BROTLI_SHARED_DICTIONARY_RAW
+            raise RuntimeError("BrotliDecoderAttachDictionary failed")
+        out = ctypes.create_string_buffer(max_out + 16)
+        avail_in, avail_out = ctypes.c_size_t(len(comp)), ctypes.c_size_t(len(out))
+        next_in = ctypes.c_void_p(ctypes.cast(ctypes.c_char_p(comp), ctypes.c_void_p).value)
+        next_out = ctypes.c_void_p(ctypes.addressof(out))
+        total = ctypes.c_size_t(0)
+        res = dec.BrotliDecoderDecompressStream(st, ctypes.byref(avail_in), ctypes.byref(next_in), ctypes.byref(avail_out),
+                                                ctypes.byref(next_out), ctypes.byref(total))
+        if res != 1:
+            raise ValueError("libbrotlidec rejected the stream (result=%d)" % res)
+        return out.raw[:len(out) - avail_out.value]
+    finally:
+        dec.BrotliDecoderDestroyInstance(st)
+
+
 class OracleStats(ctypes.Structure):
     _fields_ = [("num_metablocks", ctypes.c_size_t), ("num_commands_total", ctypes.c_size_t),
                 ("num_literals_total", ctypes.c_size_t), ("hasher_type", ctypes.c_int),

@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libbrotli_b200.so")
 SOURCES = ["bro_encoder.cu", "bro_capi.cu"]
 DEPS = ["bro_common.cuh", "bro_huffman.cuh", "bro_meta.cuh", "bro_parse.cuh", "bro_split.cuh", "bro_finalize.cuh",
-        "bro_kernels.cuh", "bro_encoder.h", "bro_dict.cuh", "bro_dict_data.inc"]
+        "bro_kernels.cuh", "bro_kernels_hq.cuh", "bro_hq.cuh", "bro_bsplit.cuh", "bro_encoder.h", "bro_dict.cuh", "bro_dict_data.inc"]
 
 
 def needs_build():

@@ -110,14 +110,36 @@ BRO_HD uint8_t utf8_lut1(uint32_t c) {
 }
 BRO_HD uint32_t context_utf8(uint8_t p1, uint8_t p2) { return utf8_lut0(p1) | utf8_lut1(p2); }
 
-// static literal context maps (encode.rs:1723-1732, 1782-1798); id 0 = no context modelling
-enum { CTXMAP_NONE = 0, CTXMAP_SIMPLE2 = 1, CTXMAP_CONT3 = 2, CTXMAP_COMPLEX13 = 3 };
-BRO_HD uint32_t ctxmap_num_contexts(int id) { return id == 0 ? 1u : id == 1 ? 2u : id == 2 ? 3u : 13u; }
+// SIGNED literal context (RFC 7932 7.1): 3-bit class of each of the two previous bytes
+BRO_HD uint32_t signed_lut(uint32_t c) {
+  if (c == 0) return 0;
+  if (c < 16) return 1;
+  if (c < 64) return 2;
+  if (c < 128) return 3;
+  if (c < 192) return 4;
+  if (c < 240) return 5;
+  if (c < 255) return 6;
+  return 7;
+}
+BRO_HD uint32_t context_signed(uint8_t p1, uint8_t p2) { return (signed_lut(p1) << 3) | signed_lut(p2); }
+
+// static literal context maps (encode.rs:1723-1732, 1782-1798); id 0 = no context modelling.  Ids 4 / 5 (quality >= 10): all 64
+// contexts of the UTF8 / SIGNED mode, mapped to prefix codes by a clustered context map (metablock.rs:133-301).
+enum { CTXMAP_NONE = 0, CTXMAP_SIMPLE2 = 1, CTXMAP_CONT3 = 2, CTXMAP_COMPLEX13 = 3, CTXMAP_FULL_UTF8 = 4, CTXMAP_FULL_SIGNED = 5 };
+BRO_HD uint32_t ctxmap_num_contexts(int id) { return id == 0 ? 1u : id == 1 ? 2u : id == 2 ? 3u : id == 3 ? 13u : 64u; }
+BRO_HD uint32_t literal_context(int id, uint8_t p1, uint8_t p2) { return id == CTXMAP_FULL_SIGNED ? context_signed(p1, p2) : context_utf8(p1, p2); }
+// context of a command's distance symbol (CommandDistanceContext, command.rs:203-215)
+BRO_HD uint32_t distance_context(uint32_t cmd_prefix) {
+  const uint32_t r = cmd_prefix >> 6, c = cmd_prefix & 7u;
+  if ((r == 0 || r == 2 || r == 4 || r == 7) && c <= 2) return c;
+  return 3;
+}
 BRO_HD uint32_t ctxmap_lookup(int id, uint32_t ctx6) {
   static constexpr uint8_t complex13[64] = {11, 11, 12, 12, 0, 0, 0, 0, 1, 1, 9, 9, 2, 2, 2, 2, 1, 1, 1, 1, 8, 3,
                                  3,  3,  1,  1,  1, 1, 2, 2, 2, 2, 8, 4, 4, 4, 8, 7, 4, 4, 8, 0, 0, 0,
                                  3,  3,  3,  3,  5, 5, 10, 5, 5, 5, 10, 5, 6, 6, 6, 6, 6, 6, 6, 6};
   if (id == CTXMAP_NONE) return 0;
+  if (id >= CTXMAP_FULL_UTF8) return ctx6;
   if (id == CTXMAP_SIMPLE2) return (ctx6 == 2 || ctx6 == 3) ? 1u : 0u;
   if (id == CTXMAP_CONT3) return ctx6 < 2 ? 1u : (ctx6 < 4 ? 2u : 0u);
   return complex13[ctx6];

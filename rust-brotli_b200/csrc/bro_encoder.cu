@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "bro_kernels.cuh"
+#include "bro_kernels_hq.cuh"
 #include "bro_encoder.h"
 #include "bro_dict_data.inc"  // generated at build time by gen_dict.py: kDictData, kDictHash
 
@@ -84,12 +85,15 @@ struct EventPool {
 struct Lane {
   cudaStream_t stream = nullptr;
   DevBuf d_sortA, d_sortB, d_hist, d_digit, d_best, d_raw, d_unit, d_cmds, d_cmd_bits, d_lit_syms, d_cmd_syms, d_dist_syms,
-      d_mb, d_split_u8, d_split_u32, d_split_counts, d_hist_lit, d_hist_cmd, d_hist_dist, d_split_codes, d_codes_u8,
+      d_hqm, d_hqn, d_hq_nodes, d_hq_pre, d_hq_scratch, d_bs_meta, d_bs_blockid, d_bs_signal, d_bs_hist, d_bs_icost, d_bs_first, d_bs_bstart,
+      d_bs_bh_in, d_bs_bh_work, d_bs_u64, d_bs_u32, d_bs_nsurv, d_cm_in, d_cm_work, d_cm_u64, d_cm_u32, d_cm_nsurv, d_cm_counts, d_cm_maps, d_mb, d_split_u8, d_split_u32, d_split_counts, d_hist_lit, d_hist_cmd, d_hist_dist, d_split_codes, d_codes_u8,
       d_codes_u16, d_hdr, d_huff_ws, d_ctxmap_ws, d_tree_ws, d_tree_bits, d_tree_nbits, d_cmd_tile, d_long_tab, d_seg_bits, d_sect_bits, d_sect_nbits;
   EventPool marks;  // timing marks: (event, stage that starts there); -1 ends the last stage
   std::vector<int> mark_stage;
   void release() {
-    DevBuf* all[] = {&d_sortA, &d_sortB, &d_hist, &d_digit, &d_best, &d_raw, &d_unit, &d_cmds, &d_cmd_bits, &d_lit_syms,
+    DevBuf* all[] = {&d_hqm, &d_hqn, &d_hq_nodes, &d_hq_pre, &d_hq_scratch, &d_bs_meta, &d_bs_blockid, &d_bs_signal, &d_bs_hist, &d_bs_icost,
+                     &d_bs_first, &d_bs_bstart, &d_bs_bh_in, &d_bs_bh_work, &d_bs_u64, &d_bs_u32, &d_bs_nsurv, &d_cm_in, &d_cm_work, &d_cm_u64,
+                     &d_cm_u32, &d_cm_nsurv, &d_cm_counts, &d_cm_maps, &d_sortA, &d_sortB, &d_hist, &d_digit, &d_best, &d_raw, &d_unit, &d_cmds, &d_cmd_bits, &d_lit_syms,
                      &d_cmd_syms, &d_dist_syms, &d_mb, &d_split_u8, &d_split_u32, &d_split_counts, &d_hist_lit, &d_hist_cmd,
                      &d_hist_dist, &d_split_codes, &d_codes_u8, &d_codes_u16, &d_hdr, &d_huff_ws, &d_ctxmap_ws, &d_tree_ws,
                      &d_tree_bits, &d_tree_nbits, &d_cmd_tile, &d_long_tab, &d_seg_bits, &d_sect_bits, &d_sect_nbits};
@@ -107,13 +111,14 @@ struct B200Encoder {
   bool ok = false;
   // configuration knobs (tests flip these)
   uint32_t unit = 4096, mb_units = 1024, lcap = 64;
-  int use_rle_opt = 1, split = 1, ctx_model = 1, use_dict = 1;
+  int use_rle_opt = 1, split = 1, ctx_model = 1, use_dict = 1, hq_split = 1;
+  uint32_t hq_unit = 16384;  // parse unit of the shortest-path parse (quality >= 10)
   int num_lanes = 4;
   int pair_parse = 4;     // parse units per warp for q5 / q6: 4 (default) or 2; 0 = one unit per warp (kept for A/B measurements)
   int shallow_match = 1;  // branch-free candidate scan for depth 16 / 32 (0: loop version, kept for A/B measurements)
   Lane lanes[kMaxLanes];
   cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams
-  DevBuf d_dict_words, d_dict_hash;
+  DevBuf d_dict_words, d_dict_hash, d_dict_lutb, d_dict_lute, d_dict_trg, d_dict_tr;
   DevBuf d_data, d_lut, d_out, d_total;          // d_total: [0] running bit position, [1 + k] position after chunk k
   uint64_t* h_total = nullptr;                   // pinned mirror of d_total[1 + k]
   size_t h_total_cap = 0;
@@ -139,6 +144,13 @@ struct B200Encoder {
     CUDA_OK(cudaMemset(d_dict_words.p, 0, sizeof(kDictData) + 64));
     CUDA_OK(cudaMemcpy(d_dict_words.p, kDictData, sizeof(kDictData), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(d_dict_hash.p, kDictHash, sizeof(kDictHash), cudaMemcpyHostToDevice));
+    if (!d_dict_lutb.ensure(sizeof(kDictLutBuckets)) || !d_dict_lute.ensure(sizeof(kDictLutEntries)) || !d_dict_trg.ensure(sizeof(kDictTrGroups)) ||
+        !d_dict_tr.ensure(sizeof(kDictTransforms)))
+      return false;
+    CUDA_OK(cudaMemcpy(d_dict_lutb.p, kDictLutBuckets, sizeof(kDictLutBuckets), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(d_dict_lute.p, kDictLutEntries, sizeof(kDictLutEntries), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(d_dict_trg.p, kDictTrGroups, sizeof(kDictTrGroups), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(d_dict_tr.p, kDictTransforms, sizeof(kDictTransforms), cudaMemcpyHostToDevice));
     CUDA_OK(cudaDeviceSetLimit(cudaLimitStackSize, 4096));
     CUDA_OK(cudaFuncSetAttribute(k_split_greedy, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_SMEM_WORDS * 4));
     for (int i = 0; i < B200_NUM_STAGES; ++i) stage_ms[i] = 0;
@@ -149,7 +161,7 @@ struct B200Encoder {
     cudaSetDevice(device);
     cudaDeviceSynchronize();
     for (auto& L : lanes) L.release();
-    DevBuf* all[] = {&d_data, &d_lut, &d_out, &d_total, &d_dict_words, &d_dict_hash};
+    DevBuf* all[] = {&d_data, &d_lut, &d_out, &d_total, &d_dict_words, &d_dict_hash, &d_dict_lutb, &d_dict_lute, &d_dict_trg, &d_dict_tr};
     for (auto* b : all) b->release();
     if (h_total) cudaFreeHost(h_total);
     sync_events.destroy();
@@ -177,7 +189,8 @@ struct B200Encoder {
     uint32_t hint = size_hint > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)size_hint;
     P->size_hint = hint;
     // ChooseHasher, encode.rs:834-893 (H40-42 are not implemented there and fall back to H6 with default params)
-    if (quality == 9) { P->hash_type = 9; P->key_bits = 15; P->hash_len = 4; P->depth = 256; P->n_last = 16; }
+    if (quality >= 10) { P->hash_type = 5; P->key_bits = 15; P->hash_len = 4; P->depth = 1024; P->n_last = 16; }  // bucket lists for k_match_all
+    else if (quality == 9) { P->hash_type = 9; P->key_bits = 15; P->hash_len = 4; P->depth = 256; P->n_last = 16; }
     else if (lgwin <= 16) { P->hash_type = 6; P->key_bits = 15; P->hash_len = 5; P->depth = 256; P->n_last = 16; }
     else if (hint > (1u << 22) && lgwin >= 19) {
       P->hash_type = 6; P->key_bits = 15; P->hash_len = 5; P->depth = 1 << (quality - 1);
@@ -195,6 +208,13 @@ struct B200Encoder {
     P->split = split;
     P->ctx_model = ctx_model;
     P->use_dict = use_dict;
+    P->hq_split = hq_split;
+    if (quality >= 10) {  // same metablock span, larger parse units
+      const uint32_t span = P->unit * P->mb_units;
+      P->unit = bmin(hq_unit, span);
+      P->mb_units = span / P->unit;
+      P->lcap = HQ_LCAP;
+    }
   }
 
   // device buffers of lane L for one chunk of `c` bytes
@@ -214,7 +234,13 @@ struct B200Encoder {
     W->max_cmd_types = P.split ? 256 : 1;
     W->max_dist_types = P.split ? 256 : 1;
     W->hdr_cap = P.split ? (384u << 10) : (16u << 10);
-    if (!L.d_best.ensure(((size_t)c + 64) * 4)) return false;
+    const bool hq = P.quality >= 10;
+    if (!hq && !L.d_best.ensure(((size_t)c + 64) * 4)) return false;
+    if (hq) {
+      if (!L.d_hqm.ensure(((size_t)c + 64) * HQ_MAXM * sizeof(HqMatch)) || !L.d_hqn.ensure((size_t)c + 64)) return false;
+      if (!L.d_hq_nodes.ensure((size_t)NU * (P.unit + 1) * sizeof(ZNode)) || !L.d_hq_pre.ensure((size_t)NU * (P.unit + 1) * 4)) return false;
+      if (!L.d_hq_scratch.ensure((size_t)NU * HQ_SCRATCH_WORDS * 4)) return false;
+    }
     if (!L.d_raw.ensure((size_t)NU * cu * sizeof(RawCmd))) return false;
     if (!L.d_unit.ensure((size_t)NU * 7 * 4)) return false;
     if (!L.d_cmds.ensure((size_t)NM * cmd_cap * sizeof(GCmd))) return false;
@@ -240,7 +266,11 @@ struct B200Encoder {
     if (!L.d_codes_u16.ensure((size_t)NM * code_syms * 2)) return false;
     if (!L.d_hdr.ensure((size_t)NM * W->hdr_cap)) return false;
     if (!L.d_huff_ws.ensure((size_t)NM * sizeof(HuffStoreWs))) return false;
-    if (!L.d_ctxmap_ws.ensure((size_t)NM * 256 * 64 * 4)) return false;
+    if (!L.d_ctxmap_ws.ensure((size_t)NM * (256 * 64 + 1024) * 4)) return false;
+    if (!L.d_cm_maps.ensure((size_t)NM * (CM_LIT_MAX + CM_DIST_MAX)) || !L.d_cm_counts.ensure((size_t)NM * 2 * 4)) return false;
+    W->lit_cmap = L.d_cm_maps.as<uint8_t>();
+    W->dist_cmap = W->lit_cmap + (size_t)NM * CM_LIT_MAX;
+    W->cm_counts = L.d_cm_counts.as<uint32_t>();
     const size_t tree_cap = (size_t)W->max_lit_trees + W->max_cmd_types + W->max_dist_types;
     if (!L.d_tree_bits.ensure((size_t)NM * tree_cap * TREE_SLOT_BYTES)) return false;
     if (!L.d_tree_nbits.ensure((size_t)NM * tree_cap * 4)) return false;
@@ -256,7 +286,14 @@ struct B200Encoder {
     W->lut = d_lut.as<uint32_t>();
     W->dict.words = d_dict_words.as<uint8_t>();
     W->dict.hash = d_dict_hash.as<uint16_t>();
+    W->dict.lut_buckets = d_dict_lutb.as<uint16_t>();
+    W->dict.lut_entries = d_dict_lute.as<uint32_t>();
+    W->dict.tr_groups = d_dict_trg.as<uint8_t>();
+    W->dict.transforms = d_dict_tr.as<uint8_t>();
+    W->dict.num_tr_groups = BRO_DICT_NUM_TR_GROUPS;
     W->best = L.d_best.as<uint32_t>();
+    W->hqm = L.d_hqm.as<HqMatch>();
+    W->hqn = L.d_hqn.as<uint8_t>();
     W->raw = L.d_raw.as<RawCmd>();
     uint32_t* up = L.d_unit.as<uint32_t>();
     W->unit_ncmd = up; W->unit_tail = up + NU; W->unit_ncopy = up + 2 * (size_t)NU;
@@ -297,6 +334,93 @@ struct B200Encoder {
     W->sect_bits = L.d_sect_bits.as<uint8_t>();
     W->sect_nbits = L.d_sect_nbits.as<uint32_t>();
     W->total_bits = d_total.as<uint64_t>();
+    return true;
+  }
+
+  // workspaces of the quality >= 10 histogram stage (BrotliSplitBlock + context-map clustering) for one chunk
+  bool ensure_hq_split(Lane& L, const Workspace& W, BsWs* B, CmWs* M) {
+    const uint32_t NM = W.num_mb;
+    const uint32_t mb_span = W.P.unit * W.P.mb_units;
+    memset(B, 0, sizeof(*B));
+    memset(M, 0, sizeof(*M));
+    B->cap[0] = mb_span; B->cap[1] = W.cmd_cap; B->cap[2] = W.cmd_cap;
+    B->maxb[0] = W.lit_blk_cap; B->maxb[1] = W.cmd_blk_cap; B->maxb[2] = W.dist_blk_cap;
+    for (int i = 0; i < 3; ++i) B->segc[i] = B->cap[i] / BS_SEG + 1;
+    B->cap_sum = B->cap[0] + B->cap[1] + B->cap[2];
+    B->maxb_sum = B->maxb[0] + B->maxb[1] + B->maxb[2];
+    B->segc_sum = B->segc[0] + B->segc[1] + B->segc[2];
+    B->bh_sum = B->maxb[0] * 256 + B->maxb[1] * 704 + B->maxb[2] * 64;
+    B->nsurv_stride = std::max(B->maxb[0], std::max(B->maxb[1], B->maxb[2])) / 64 + 2;
+    const size_t nb = (size_t)NM * B->maxb_sum;
+    if (!L.d_bs_meta.ensure((size_t)NM * 3 * sizeof(BsMeta)) || !L.d_bs_blockid.ensure((size_t)NM * B->cap_sum + 64) ||
+        !L.d_bs_signal.ensure((size_t)NM * B->cap_sum * 16 + 64) || !L.d_bs_hist.ensure((size_t)NM * 102400 * 4) ||
+        !L.d_bs_icost.ensure((size_t)NM * 102400 * 4) || !L.d_bs_first.ensure((size_t)NM * 3 * 128 * 4) || !L.d_bs_bstart.ensure((nb + NM * 3) * 4 + 64) ||
+        !L.d_bs_bh_in.ensure((size_t)NM * B->bh_sum * 4) || !L.d_bs_bh_work.ensure((size_t)NM * B->bh_sum * 4) || !L.d_bs_u64.ensure(nb * 2 * 8) ||
+        !L.d_bs_u32.ensure(nb * 4 * 4) || !L.d_bs_nsurv.ensure((size_t)NM * 3 * B->nsurv_stride * 4))
+      return false;
+    B->meta = L.d_bs_meta.as<BsMeta>();
+    B->blockid = L.d_bs_blockid.as<uint8_t>();
+    B->signal = L.d_bs_signal.as<uint32_t>();
+    B->hist = L.d_bs_hist.as<uint32_t>();
+    B->icost = L.d_bs_icost.as<uint32_t>();
+    B->firstpos = L.d_bs_first.as<uint32_t>();
+    B->bstart = L.d_bs_bstart.as<uint32_t>();
+    B->bh_in = L.d_bs_bh_in.as<uint32_t>();
+    B->bh_work = L.d_bs_bh_work.as<uint32_t>();
+    B->ccost = L.d_bs_u64.as<uint64_t>();
+    B->bd = reinterpret_cast<int64_t*>(B->ccost + nb);
+    B->csize = L.d_bs_u32.as<uint32_t>(); B->hsym = B->csize + nb; B->clusters = B->hsym + nb; B->bj = B->clusters + nb;
+    B->nsurv = L.d_bs_nsurv.as<uint32_t>();
+    const size_t nc = (size_t)NM * (CM_LIT_MAX + CM_DIST_MAX);
+    const size_t hl = (size_t)NM * CM_LIT_MAX * 256, hd = (size_t)NM * CM_DIST_MAX * 64;
+    if (!L.d_cm_in.ensure((hl + hd) * 4) || !L.d_cm_work.ensure((hl + hd) * 4) || !L.d_cm_u64.ensure(nc * 2 * 8) || !L.d_cm_u32.ensure(nc * 4 * 4) ||
+        !L.d_cm_nsurv.ensure((size_t)NM * 2 * CM_NSURV_STRIDE * 4))
+      return false;
+    M->in_lit = L.d_cm_in.as<uint32_t>(); M->in_dist = M->in_lit + hl;
+    M->work_lit = L.d_cm_work.as<uint32_t>(); M->work_dist = M->work_lit + hl;
+    M->cost = L.d_cm_u64.as<uint64_t>();
+    M->bd = reinterpret_cast<int64_t*>(M->cost + nc);
+    M->size = L.d_cm_u32.as<uint32_t>(); M->sym = M->size + nc; M->clusters = M->sym + nc; M->bj = M->clusters + nc;
+    M->nsurv = L.d_cm_nsurv.as<uint32_t>();
+    M->counts = W.cm_counts;
+    M->lit_cmap = W.lit_cmap;
+    M->dist_cmap = W.dist_cmap;
+    return true;
+  }
+  // BrotliSplitBlock + BrotliBuildMetaBlock's clustering for every metablock of the chunk (replaces k_split_greedy)
+  bool run_hq_split(Lane& L, const Workspace& W) {
+    BsWs B;
+    CmWs M;
+    if (!ensure_hq_split(L, W, &B, &M)) return false;
+    cudaStream_t st = L.stream;
+    const uint32_t NM = W.num_mb;
+    const dim3 g3(NM, 3), gx3(64, NM, 3), g2(NM, 2), gx2(64, NM, 2);
+    k_bs_setup<<<g3, 128, 0, st>>>(W, B);
+    k_bs_sample<<<dim3(32, NM, 3), 256, 0, st>>>(W, B);
+    for (int it = 0; it < 3; ++it) {
+      k_bs_icost<<<g3, 256, 0, st>>>(W, B);
+      k_bs_forward<<<dim3(B.segc[0], NM, 3), 32, 0, st>>>(W, B);
+      k_bs_backward<<<g3, 32, 0, st>>>(W, B);
+      k_bs_remap<<<g3, 256, 0, st>>>(W, B);
+      k_bs_rehist<<<gx3, 256, 0, st>>>(W, B);
+    }
+    k_bs_blocks<<<g3, 1024, 0, st>>>(W, B);
+    CUDA_OK(cudaMemsetAsync(B.bh_in, 0, (size_t)NM * B.bh_sum * 4, st));
+    k_bs_bhist<<<gx3, 256, 0, st>>>(W, B);
+    k_bs_cl_prepare<<<gx3, CL_WARPS * 32, 0, st>>>(W, B);
+    k_bs_cl_batch<<<dim3(32, NM, 3), CL_WARPS * 32, 0, st>>>(W, B);
+    k_bs_cl_final<<<g3, 32, 0, st>>>(W, B);
+    k_bs_cl_assign<<<gx3, CL_WARPS * 32, 0, st>>>(W, B);
+    k_bs_types<<<g3, 32, 0, st>>>(W, B);
+    k_cm_zero<<<dim3(64, NM), 256, 0, st>>>(W, M);
+    k_cm_hist<<<gx3, 256, 0, st>>>(W, M);
+    k_cm_cl_prepare<<<gx2, CL_WARPS * 32, 0, st>>>(W, M);
+    k_cm_cl_batch<<<gx2, CL_WARPS * 32, 0, st>>>(W, M);
+    k_cm_cl_final<<<g2, 32, 0, st>>>(W, M);
+    k_cm_cl_assign<<<gx2, CL_WARPS * 32, 0, st>>>(W, M);
+    k_cm_reindex<<<g2, 256, 0, st>>>(W, M);
+    k_cm_rebuild<<<gx2, 256, 0, st>>>(W, M);
+    launches += 2 + 15 + 3 + 5 + 8;
     return true;
   }
 
@@ -389,6 +513,15 @@ struct B200Encoder {
       const size_t smem = (size_t)(MATCH_THREADS + P.depth) * 6 * 4;
       mark(L, B200_ST_MATCH);
       const uint32_t mgrid = (count + MATCH_THREADS - 1) / MATCH_THREADS;
+      if (P.quality >= 10) {  // all matches of every position
+        MatchAllArgs aa;
+        aa.m = ma;
+        aa.hqm = W.hqm - (size_t)range_start * HQ_MAXM;
+        aa.hqn = W.hqn - range_start;
+        aa.quality = P.quality;
+        if (P.depth != 1024) { fprintf(stderr, "[brotli_b200] unsupported bucket depth %d\n", P.depth); return false; }
+        k_match_all<1024><<<mgrid, MATCH_THREADS, (size_t)(MATCH_THREADS + 1024) * 3 * 4, stream>>>(aa);
+      } else
       switch (P.depth) {  // bucket depth = 1 << block_bits: 16 (q5) .. 256 (q9, and lgwin <= 16)
         case 16:
           if (shallow_match) k_match_shallow<16><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
@@ -406,6 +539,13 @@ struct B200Encoder {
       launches += 1;
     }
     mark(L, B200_ST_PARSE);
+    if (P.quality >= 10) {  // shortest-path parse, one unit per warp
+      ZopfliArgs za;
+      za.nodes = L.d_hq_nodes.as<ZNode>();
+      za.pre = L.d_hq_pre.as<uint32_t>();
+      za.scratch = L.d_hq_scratch.as<uint32_t>();
+      k_zopfli<<<W.num_units, 32, 0, stream>>>(W, za);
+    } else
     if (pair_parse == 4 && P.n_last == 4 && P.hash_type != 9)  // four units per warp (q5, q6)
       k_parse_pair<4><<<(W.num_units + 4 * PARSE_WARPS - 1) / (4 * PARSE_WARPS), PARSE_WARPS * 32, 0, stream>>>(W);
     else if (pair_parse && P.n_last == 4 && P.hash_type != 9)  // two units per warp
@@ -426,7 +566,8 @@ struct B200Encoder {
     mark(L, B200_ST_SPLIT);
     {
       dim3 g(W.num_mb, 3);
-      if (P.split) k_split_greedy<<<g, SPLIT_THREADS, SPLIT_SMEM_WORDS * 4, stream>>>(W);
+      if (P.quality >= 10 && P.hq_split) { if (!run_hq_split(L, W)) return false; }
+      else if (P.split) k_split_greedy<<<g, SPLIT_THREADS, SPLIT_SMEM_WORDS * 4, stream>>>(W);
       else k_split_simple<<<g, 512, 0, stream>>>(W);
     }
     mark(L, B200_ST_HEADER);
@@ -467,11 +608,11 @@ int b200_device_count(void) {
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
   return n;
 }
-// The quality the device path runs for a requested one: 5..9 hash-chain family (encode.rs:834-893), 10 / 11 optimal parse;
+// The quality the device path runs for a requested one: 5..9 hash-chain family (encode.rs:834-893), 10 / 11 shortest-path parse;
 // q0..q4 (BasicHasher H2..H54, fragment compressors) are not built and run as 5.
 int b200_effective_quality(int requested_quality) {
   if (requested_quality < 5) return 5;
-  if (requested_quality > 9) return 9;
+  if (requested_quality > 11) return 11;
   return requested_quality;
 }
 
@@ -501,6 +642,8 @@ int b200_encoder_set_option(B200Encoder* e, int option, uint32_t value) {
     case B200_OPT_DICT: e->use_dict = (int)value; return 1;
     case B200_OPT_SHALLOW_MATCH: e->shallow_match = (int)value; return 1;
     case B200_OPT_PAIR_PARSE: e->pair_parse = (int)value; return 1;
+    case B200_OPT_HQ_SPLIT: e->hq_split = (int)value; return 1;
+    case B200_OPT_HQ_UNIT: e->hq_unit = value; return 1;
     case B200_OPT_LANES: e->num_lanes = value < 1 ? 1 : (value > (uint32_t)kMaxLanes ? kMaxLanes : (int)value); return 1;
   }
   return 0;
@@ -636,6 +779,27 @@ int b200_stage_match(B200Encoder* e, int quality, int lgwin, const uint8_t* in, 
     return 0;
   }
   return cudaMemcpy(best_out, e->lanes[0].d_best.p, n * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+}
+
+// test hook (quality >= 10): matches per position, per-unit results and raw commands of an n-byte buffer (n <= one chunk)
+int b200_stage_hq(B200Encoder* e, int quality, int lgwin, const uint8_t* in, size_t n, uint8_t* hqn, uint32_t* hqm, uint32_t* units,
+                  uint32_t* raw) {
+  if (!e || !e->ok || n == 0 || n > kChunk || quality < 10) return 0;
+  if (cudaSetDevice(e->device) != cudaSuccess) return 0;
+  size_t got = 0;
+  if (!compress_range_impl(e, quality, lgwin, n, in, n, 0, n, true, true, false, nullptr, b200_max_compressed_size(n) + 64, &got, 0, true)) {
+    cudaDeviceSynchronize();
+    return 0;
+  }
+  EncParams P;
+  e->fill_params(&P, quality, lgwin, n);
+  const uint32_t nu = (uint32_t)((n + P.unit - 1) / P.unit);
+  Lane& L = e->lanes[0];
+  bool ok = cudaMemcpy(hqn, L.d_hqn.p, n, cudaMemcpyDeviceToHost) == cudaSuccess;
+  ok = ok && cudaMemcpy(hqm, L.d_hqm.p, n * HQ_MAXM * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
+  ok = ok && cudaMemcpy(units, L.d_unit.p, (size_t)nu * 3 * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+  ok = ok && cudaMemcpy(raw, L.d_raw.p, (size_t)nu * (P.unit / 2 + 1) * 12, cudaMemcpyDeviceToHost) == cudaSuccess;
+  return ok ? 1 : 0;
 }
 
 }  // extern "C"

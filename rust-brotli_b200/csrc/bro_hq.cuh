@@ -1,0 +1,533 @@
+// bro_hq.cuh -- quality 10 / 11: all matches per position, literal cost estimate, shortest-path ("Zopfli") parse.
+//
+// Reference semantics: FindAllMatchesH10 (backward_references/hq.rs:302-417) on top of the H10 binary tree
+// (hash_to_binary_tree.rs:437-530), BrotliEstimateBitCostsForLiterals (literal_cost.rs), ZopfliCostModel (hq.rs:167-252,
+// :1046-1154), UpdateNodes / EvaluateNode / StartPosQueue (hq.rs:419-821), ZopfliIterate (:1157),
+// BrotliCreateHqZopfliBackwardReferences (:1237), BrotliZopfliCreateCommands (:97).
+//
+// B200 re-design:
+//  * The mutating binary tree is replaced by the position-ordered bucket lists the sort stage already builds: a position's
+//    matches are the Pareto front (longer => farther) over the short-range scan, the `depth` nearest earlier positions of
+//    its bucket that share its first four bytes, and the static-dictionary candidate.  Every position is independent.
+//  * The shortest-path parse runs per parse unit (32 / 64 KiB instead of the reference's 256 KiB input block), units are
+//    independent: each starts from an unknown distance cache and its copies stop at its end; the finalise stage assigns the
+//    real short codes from the true distance sequence and merges copies that continue across a seam (bro_finalize.cuh).
+//  * Costs are Q10 fixed point (u32) instead of f32, so the result does not depend on evaluation order or on the machine.
+// Everything in this header is a per-position or per-unit sequential routine (one GPU thread, or the CPU model).
+#pragma once
+#include "bro_common.cuh"
+#include "bro_parse.cuh"
+
+namespace bro {
+
+#ifndef HQ_MAXW
+#define HQ_MAXW 8u           // window matches kept per position (the longest ones)
+#endif
+#ifndef HQ_MAXD
+#define HQ_MAXD 8u           // dictionary matches kept per position (the longest ones)
+#endif
+#define HQ_MAXM (HQ_MAXW + HQ_MAXD)
+#define HQ_LCAP 384u         // match length cap of the all-matches stage (> MaxZopfliLen = 325); longer copies are extended by the parse
+#define HQ_QBITS 10          // cost fixed point
+#define HQ_ONE (1u << HQ_QBITS)
+#define HQ_INF 0xFFFFFFFFu
+
+struct HqMatch {
+  uint32_t dist;  // backward distance; for a dictionary match: word_id (index + (transform << NDBITS[len]))
+  uint32_t lc;    // bits 0..15 bytes produced, bits 16..20 word length (dictionary), bit 31 dictionary
+};
+BRO_HD uint32_t hqm_len(const HqMatch& m) { return m.lc & 0xFFFFu; }
+BRO_HD bool hqm_is_dict(const HqMatch& m) { return (m.lc >> 31) != 0; }
+BRO_HD uint32_t hqm_len_code(const HqMatch& m) { return hqm_is_dict(m) ? ((m.lc >> 16) & 31u) : (m.lc & 0xFFFFu); }
+
+BRO_HD int hq_max_candidates(int quality) { return quality <= 10 ? 1 : 5; }          // hq.rs:417-419
+BRO_HD uint32_t hq_max_zopfli_len(int quality) { return quality <= 10 ? 150u : 325u; }  // hq.rs:159-165
+BRO_HD uint32_t hq_short_back(int quality) { return quality != 11 ? 16u : 64u; }      // hq.rs:325-329
+
+// common-prefix length of a[..] and b[..], at most max_len (device: 8 bytes at a time; the input has >= 512 B of padding)
+BRO_HD uint32_t hq_lcp(const uint8_t* a, const uint8_t* b, uint32_t max_len) {
+#ifdef __CUDA_ARCH__
+  uint32_t i = 0;
+  while (i + 8 <= max_len) {
+    uint64_t x, y;
+    memcpy(&x, a + i, 8);
+    memcpy(&y, b + i, 8);
+    x ^= y;
+    if (x) return i + ((uint32_t)(__ffsll((long long)x) - 1) >> 3);
+    i += 8;
+  }
+  while (i < max_len && a[i] == b[i]) ++i;
+  return i;
+#else
+  return lcp_bytes(a, b, max_len);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------
+// All matches of one position.
+// ---------------------------------------------------------------------------------------------------
+struct HqMatchList {
+  HqMatch m[HQ_MAXM];
+  uint32_t n;
+  uint32_t best_len;
+};
+BRO_HD void hq_list_init(HqMatchList& L) { L.n = 0; L.best_len = 1; }
+BRO_HD void hq_push(HqMatchList& L, uint32_t dist, uint32_t lc) {
+  if (L.n == HQ_MAXW) {  // full: drop the shortest
+    for (uint32_t k = 0; k + 1 < HQ_MAXW; ++k) L.m[k] = L.m[k + 1];
+    L.n = HQ_MAXW - 1;
+  }
+  L.m[L.n].dist = dist;
+  L.m[L.n].lc = lc;
+  ++L.n;
+}
+// 2- and 3-byte matches at very short distances, which no 4-byte hash can find (hq.rs:325-356)
+BRO_HD void hq_short_matches(const uint8_t* cur, uint32_t max_len, uint32_t max_backward, uint32_t short_back, HqMatchList& L) {
+  for (uint32_t back = 1; back < short_back && L.best_len <= 2; ++back) {
+    if (back > max_backward) break;
+    const uint8_t* prev = cur - back;
+    if (cur[0] == prev[0] && cur[1] == prev[1]) {
+      const uint32_t len = hq_lcp(prev, cur, max_len);
+      if (len > L.best_len) {
+        L.best_len = len;
+        hq_push(L, back, len);
+      }
+    }
+  }
+}
+// One bucket candidate at distance `backward` that is known to share the first four bytes.  Returns false when the walk can
+// stop (a full-length match: nothing farther can be longer).
+BRO_HD bool hq_bucket_candidate(const uint8_t* cur, uint32_t backward, uint32_t max_len, HqMatchList& L) {
+  const uint8_t* prev = cur - backward;
+  if (L.best_len < max_len && prev[L.best_len] != cur[L.best_len]) return true;  // cannot be strictly longer
+  const uint32_t len = hq_lcp(prev, cur, max_len);
+  if (len > L.best_len) {
+    L.best_len = len;
+    hq_push(L, backward, len);
+  }
+  return len < max_len;
+}
+// static-dictionary matches (hq.rs:372-404): every produced length above the longest window match, the HQ_MAXD longest kept
+BRO_HD void hq_dict_matches(const DictView& D, const uint8_t* cur, uint32_t max_len, HqMatchList& L) {
+  uint32_t dm[DICT_MAX_MATCH_LEN + 1];
+  const uint32_t minlen = bmax(4u, L.best_len + 1u);
+  if (!dict_all_matches(D, cur, minlen, max_len, dm)) return;
+  const uint32_t maxlen = bmin(DICT_MAX_MATCH_LEN, max_len);
+  uint32_t cnt = 0;
+  for (uint32_t l = minlen; l <= maxlen; ++l) cnt += dm[l] < DICT_NO_MATCH;
+  for (uint32_t l = minlen; l <= maxlen; ++l) {
+    if (dm[l] >= DICT_NO_MATCH) continue;
+    if (cnt-- > HQ_MAXD) continue;  // more than HQ_MAXD lengths: the shortest are dropped
+    L.m[L.n].dist = dm[l] >> 5;
+    L.m[L.n].lc = l | ((dm[l] & 31u) << 16) | 0x80000000u;
+    ++L.n;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Literal cost estimate of one unit (literal_cost.rs with the unit as the block): Q10 bits per position as exclusive
+// prefix sums pre[0..len], pre[0] = 0.  hist: scratch of 3 * 256 u32.
+// ---------------------------------------------------------------------------------------------------
+BRO_HD uint32_t hq_utf8_position(uint32_t last, uint32_t c, uint32_t clamp) {  // literal_cost.rs:8-19
+  if (c < 128) return 0;
+  if (c >= 192) return bmin(1u, clamp);
+  if (last < 0xe0) return 0;
+  return bmin(2u, clamp);
+}
+BRO_HD bool hq_is_mostly_utf8(const uint8_t* d, uint32_t len) {  // utf8_util.rs:4-73, min_fraction 0.75
+  uint32_t size_utf8 = 0, i = 0;
+  while (i < len) {
+    const uint32_t left = len - i;
+    const uint8_t c0 = d[i];
+    uint32_t n = 1;
+    bool ok = false;
+    if ((c0 & 0x80) == 0) { ok = c0 > 0; }
+    if (!ok && left > 1 && (c0 & 0xe0) == 0xc0 && (d[i + 1] & 0xc0) == 0x80) {
+      const uint32_t s = ((uint32_t)(c0 & 0x1f) << 6) | (d[i + 1] & 0x3f);
+      if (s > 0x7f) { ok = true; n = 2; }
+    }
+    if (!ok && left > 2 && (c0 & 0xf0) == 0xe0 && (d[i + 1] & 0xc0) == 0x80 && (d[i + 2] & 0xc0) == 0x80) {
+      const uint32_t s = ((uint32_t)(c0 & 0x0f) << 12) | ((uint32_t)(d[i + 1] & 0x3f) << 6) | (d[i + 2] & 0x3f);
+      if (s > 0x7ff) { ok = true; n = 3; }
+    }
+    if (!ok && left > 3 && (c0 & 0xf8) == 0xf0 && (d[i + 1] & 0xc0) == 0x80 && (d[i + 2] & 0xc0) == 0x80 && (d[i + 3] & 0xc0) == 0x80) {
+      const uint32_t s = ((uint32_t)(c0 & 0x07) << 18) | ((uint32_t)(d[i + 1] & 0x3f) << 12) | ((uint32_t)(d[i + 2] & 0x3f) << 6) | (d[i + 3] & 0x3f);
+      if (s > 0xffff && s <= 0x10ffff) { ok = true; n = 4; }
+    }
+    if (ok) size_utf8 += n;
+    i += n;
+  }
+  return (uint64_t)size_utf8 * 4 > (uint64_t)len * 3;
+}
+BRO_HD uint32_t hq_lit_cost_q(const uint32_t* lut, uint32_t in_window, uint32_t histo, uint32_t i, bool ramp) {
+  if (histo == 0) histo = 1;
+  uint32_t c = ((log2_q16(lut, in_window) - log2_q16(lut, histo)) >> (16 - HQ_QBITS)) + 30u;  // + 0.02905
+  if (c < HQ_ONE) c = (c >> 1) + (HQ_ONE >> 1);
+  if (ramp && i < 2000) c += 717u - ((2000u - i) * 358u) / 2000u;  // + 0.7 - (2000 - i) / 2000 * 0.35
+  return c;
+}
+BRO_HD_NOINLINE void hq_literal_costs_unit(const uint8_t* d, uint32_t len, const uint32_t* lut, bool ramp, uint32_t* hist, uint32_t* pre) {
+  pre[0] = 0;
+  if (len == 0) return;
+  if (hq_is_mostly_utf8(d, len)) {
+    // DecideMultiByteStatsLevel, literal_cost.rs:21-48
+    uint32_t counts[3] = {0, 0, 0}, max_utf8 = 1, last_c = 0;
+    for (uint32_t i = 0; i < len; ++i) {
+      const uint32_t c = d[i];
+      ++counts[hq_utf8_position(last_c, c, 2)];
+      last_c = c;
+    }
+    if (counts[2] < 500) max_utf8 = 1;
+    if (counts[1] + counts[2] < 25) max_utf8 = 0;
+    const uint32_t window_half = 495;
+    const uint32_t in_window = bmin(window_half, len);
+    uint32_t in_window_utf8[3] = {0, 0, 0};
+    for (uint32_t i = 0; i < 3 * 256; ++i) hist[i] = 0;
+    {
+      uint32_t lc = 0, up = 0;
+      for (uint32_t i = 0; i < in_window; ++i) {
+        const uint32_t c = d[i];
+        ++hist[up * 256 + c];
+        ++in_window_utf8[up];
+        up = hq_utf8_position(lc, c, max_utf8);
+        lc = c;
+      }
+    }
+    for (uint32_t i = 0; i < len; ++i) {
+      if (i >= window_half) {
+        const uint32_t c = i < window_half + 1 ? 0u : d[i - window_half - 1];
+        const uint32_t lc = i < window_half + 2 ? 0u : d[i - window_half - 2];
+        const uint32_t up2 = hq_utf8_position(lc, c, max_utf8);
+        --hist[up2 * 256 + d[i - window_half]];
+        --in_window_utf8[up2];
+      }
+      if (i + window_half < len) {
+        const uint32_t c = d[i + window_half - 1], lc = d[i + window_half - 2];
+        const uint32_t up2 = hq_utf8_position(lc, c, max_utf8);
+        ++hist[up2 * 256 + d[i + window_half]];
+        ++in_window_utf8[up2];
+      }
+      const uint32_t c = i < 1 ? 0u : d[i - 1], lc = i < 2 ? 0u : d[i - 2];
+      const uint32_t up = hq_utf8_position(lc, c, max_utf8);
+      pre[i + 1] = pre[i] + hq_lit_cost_q(lut, in_window_utf8[up], hist[up * 256 + d[i]], i, ramp);
+    }
+  } else {
+    const uint32_t window_half = 2000;
+    uint32_t in_window = bmin(window_half, len);
+    for (uint32_t i = 0; i < 256; ++i) hist[i] = 0;
+    for (uint32_t i = 0; i < in_window; ++i) ++hist[d[i]];
+    for (uint32_t i = 0; i < len; ++i) {
+      if (i >= window_half) { --hist[d[i - window_half]]; --in_window; }
+      if (i + window_half < len) { ++hist[d[i + window_half]]; ++in_window; }
+      pre[i + 1] = pre[i] + hq_lit_cost_q(lut, in_window, hist[d[i]], i, ramp);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Cost model (hq.rs:167-252 first pass; :1046-1154 second pass of quality 11).
+// ---------------------------------------------------------------------------------------------------
+struct HqCostModel {
+  uint32_t cost_cmd[704];
+  uint32_t cost_dist[64];
+  uint32_t min_cost_cmd;
+};
+BRO_HD uint32_t hq_log2_q(const uint32_t* lut, uint32_t v) { return (log2_q16(lut, v) + (1u << (15 - HQ_QBITS))) >> (16 - HQ_QBITS); }
+BRO_HD_NOINLINE void hq_model_initial(HqCostModel* M, const uint32_t* lut) {
+  for (uint32_t i = 0; i < 704; ++i) M->cost_cmd[i] = hq_log2_q(lut, 11 + i);
+  for (uint32_t i = 0; i < 64; ++i) M->cost_dist[i] = hq_log2_q(lut, 20 + i);
+  M->min_cost_cmd = hq_log2_q(lut, 11);
+}
+// SetCost, hq.rs:1046-1074
+BRO_HD void hq_set_cost(const uint32_t* histogram, uint32_t size, bool literal_histogram, const uint32_t* lut, uint32_t* cost) {
+  uint32_t sum = 0;
+  for (uint32_t i = 0; i < size; ++i) sum += histogram[i];
+  const uint32_t log2sum = hq_log2_q(lut, sum);
+  uint32_t missing = sum;
+  if (!literal_histogram)
+    for (uint32_t i = 0; i < size; ++i) if (histogram[i] == 0) ++missing;
+  const uint32_t missing_cost = hq_log2_q(lut, missing) + 2 * HQ_ONE;
+  for (uint32_t i = 0; i < size; ++i) {
+    if (histogram[i] == 0) { cost[i] = missing_cost; continue; }
+    const uint32_t l = hq_log2_q(lut, histogram[i]);
+    uint32_t c = log2sum > l ? log2sum - l : 0;
+    if (c < HQ_ONE) c = HQ_ONE;
+    cost[i] = c;
+  }
+}
+
+// second pass: costs from the histograms of the first pass; literal prefix sums are rebuilt from the per-symbol costs
+BRO_HD_NOINLINE void hq_model_from_stats(HqCostModel* M, const uint32_t* stats, const uint32_t* lut, const uint8_t* d, uint32_t len,
+                                         uint32_t* cost_literal /* scratch [256] */, uint32_t* pre) {
+  hq_set_cost(stats, 256, true, lut, cost_literal);
+  hq_set_cost(stats + 256, 704, false, lut, M->cost_cmd);
+  hq_set_cost(stats + 256 + 704, 64, false, lut, M->cost_dist);
+  uint32_t mn = M->cost_cmd[0];
+  for (uint32_t i = 1; i < 704; ++i) mn = bmin(mn, M->cost_cmd[i]);
+  M->min_cost_cmd = mn;
+  pre[0] = 0;
+  for (uint32_t i = 0; i < len; ++i) pre[i + 1] = pre[i] + cost_literal[d[i]];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Shortest path over one unit.
+// ---------------------------------------------------------------------------------------------------
+struct ZNode {  // hash_to_binary_tree.rs:24-33
+  uint32_t length;               // copy length | (copy length + 9 - length code) << 25
+  uint32_t distance;
+  uint32_t dcode_insert_length;  // insert length | (distance short code + 1) << 27
+  uint32_t u;                    // cost (Q10) while ahead of the sweep, then the distance-cache shortcut, then `next`
+};
+BRO_HD uint32_t zn_copy_length(const ZNode& n) { return n.length & 0x1FFFFFFu; }
+BRO_HD uint32_t zn_length_code(const ZNode& n) { return zn_copy_length(n) + 9u - (n.length >> 25); }
+BRO_HD uint32_t zn_insert_length(const ZNode& n) { return n.dcode_insert_length & 0x7FFFFFFu; }
+BRO_HD uint32_t zn_distance_code(const ZNode& n) {
+  const uint32_t sc = n.dcode_insert_length >> 27;
+  return sc == 0 ? n.distance + 15u : sc - 1u;
+}
+
+struct HqPosData {
+  uint32_t pos;
+  int32_t dc[4];
+  int64_t costdiff;
+  uint32_t cost;
+};
+struct HqQueue {  // StartPosQueue, hq.rs:185-188, :493-509
+  HqPosData q[8];
+  uint32_t idx;
+};
+BRO_HD uint32_t hq_queue_size(const HqQueue& Q) { return bmin(Q.idx, 8u); }
+BRO_HD const HqPosData& hq_queue_at(const HqQueue& Q, uint32_t k) { return Q.q[(k - Q.idx) & 7u]; }
+BRO_HD void hq_queue_push(HqQueue& Q, const HqPosData& pd) {
+  uint32_t offset = ~Q.idx & 7u;
+  ++Q.idx;
+  const uint32_t len = hq_queue_size(Q);
+  Q.q[offset] = pd;
+  for (uint32_t i = 1; i < len; ++i) {
+    if (Q.q[offset & 7u].costdiff > Q.q[(offset + 1) & 7u].costdiff) {
+      const HqPosData t = Q.q[offset & 7u];
+      Q.q[offset & 7u] = Q.q[(offset + 1) & 7u];
+      Q.q[(offset + 1) & 7u] = t;
+    }
+    ++offset;
+  }
+}
+
+struct HqUnit {  // everything UpdateNodes needs about the unit being parsed
+  const uint8_t* data;     // range-relative base pointer
+  uint32_t ustart, len;    // unit = data[ustart, ustart + len)
+  uint64_t abs_base;       // absolute stream position of data[0]
+  uint32_t max_backward;   // window limit
+  int quality;
+  const HqCostModel* model;
+  const uint32_t* lit_pre; // [len + 1]
+  const int32_t* start_dc; // [4]
+  ZNode* nodes;            // [len + 1]
+};
+BRO_HD uint32_t hq_max_distance(const HqUnit& U, uint32_t pos) {
+  const uint64_t a = U.abs_base + U.ustart + pos;
+  return a < U.max_backward ? (uint32_t)a : U.max_backward;
+}
+BRO_HD uint32_t hq_shortcut(const HqUnit& U, uint32_t pos) {  // ComputeDistanceShortcut, hq.rs:421-447
+  const ZNode& n = U.nodes[pos];
+  const uint32_t clen = zn_copy_length(n), ilen = zn_insert_length(n), dist = n.distance;
+  if (pos == 0) return 0;
+  if ((uint64_t)dist + clen <= U.abs_base + U.ustart + pos && dist <= U.max_backward && zn_distance_code(n) > 0) return pos;
+  return U.nodes[pos - clen - ilen].u;
+}
+BRO_HD void hq_distance_cache(const HqUnit& U, uint32_t pos, int32_t* dc) {  // ComputeDistanceCache, hq.rs:456-490
+  int idx = 0;
+  uint32_t p = U.nodes[pos].u;
+  while (idx < 4 && p > 0) {
+    const ZNode& n = U.nodes[p];
+    dc[idx++] = (int32_t)n.distance;
+    p = U.nodes[p - zn_copy_length(n) - zn_insert_length(n)].u;
+  }
+  for (int k = 0; idx < 4; ++idx, ++k) dc[idx] = U.start_dc[k];
+}
+BRO_HD void hq_evaluate_node(const HqUnit& U, uint32_t pos, HqQueue& Q) {  // EvaluateNode, hq.rs:511-548
+  const uint32_t node_cost = U.nodes[pos].u;
+  U.nodes[pos].u = hq_shortcut(U, pos);
+  if (node_cost <= U.lit_pre[pos]) {
+    HqPosData pd;
+    pd.pos = pos;
+    pd.cost = node_cost;
+    pd.costdiff = (int64_t)node_cost - (int64_t)U.lit_pre[pos];
+    hq_distance_cache(U, pos, pd.dc);
+    hq_queue_push(Q, pd);
+  }
+}
+BRO_HD void hq_update_node(ZNode* nodes, uint32_t pos, uint32_t start_pos, uint32_t len, uint32_t len_code, uint32_t dist,
+                           uint32_t short_code, uint32_t cost) {  // UpdateZopfliNode, hq.rs:619-636
+  ZNode& next = nodes[pos + len];
+  next.length = len | ((len + 9u - len_code) << 25);
+  next.distance = dist;
+  next.dcode_insert_length = (pos - start_pos) | (short_code << 27);
+  next.u = cost;
+}
+// UpdateNodes, hq.rs:644-821.  matches[0..num_matches) sorted by length ascending.  Returns the longest copy that improved a
+// node.
+BRO_HD_NOINLINE uint32_t hq_update_nodes(const HqUnit& U, uint32_t pos, const HqMatch* matches, uint32_t num_matches, HqQueue& Q) {
+  const uint8_t* cur = U.data + U.ustart + pos;
+  const uint32_t max_distance = hq_max_distance(U, pos);
+  const uint32_t max_len = U.len - pos;
+  const uint32_t max_zopfli_len = hq_max_zopfli_len(U.quality);
+  const HqCostModel& M = *U.model;
+  ZNode* nodes = U.nodes;
+  uint32_t result = 0;
+  hq_evaluate_node(U, pos, Q);
+  uint32_t min_len;
+  {
+    const HqPosData& pd = hq_queue_at(Q, 0);
+    uint64_t min_cost = (uint64_t)pd.cost + M.min_cost_cmd + (U.lit_pre[pos] - U.lit_pre[pd.pos]);
+    // ComputeMinimumCopyLength, hq.rs:564-589
+    uint32_t len = 2, next_len_bucket = 4, next_len_offset = 10;
+    while (pos + len <= U.len && nodes[pos + len].u <= min_cost) {
+      ++len;
+      if (len == next_len_offset) {
+        min_cost += HQ_ONE;
+        next_len_offset += next_len_bucket;
+        next_len_bucket *= 2;
+      }
+    }
+    min_len = len;
+  }
+  const uint32_t ncand = bmin((uint32_t)hq_max_candidates(U.quality), hq_queue_size(Q));
+  for (uint32_t k = 0; k < ncand; ++k) {
+    const HqPosData& pd = hq_queue_at(Q, k);
+    const uint32_t start = pd.pos;
+    const uint32_t inscode = insert_length_code(pos - start);
+    const int64_t base_cost = pd.costdiff + ((int64_t)ins_extra(inscode) << HQ_QBITS) + (int64_t)U.lit_pre[pos];
+    uint32_t best_len = min_len - 1;
+    for (int j = 0; j < 16 && best_len < max_len; ++j) {
+      const int32_t backward_s = cache_candidate(pd.dc, j);  // kDistanceCacheIndex / Offset, mod.rs:653-655
+      if (backward_s <= 0 || (uint32_t)backward_s > max_distance) continue;
+      const uint32_t backward = (uint32_t)backward_s;
+      const uint8_t* prev = cur - backward;
+      if (cur[best_len] != prev[best_len]) continue;
+      const uint32_t len = hq_lcp(prev, cur, max_len);
+      const int64_t dist_cost = base_cost + M.cost_dist[j];
+      for (uint32_t l = best_len + 1; l <= len; ++l) {
+        const uint32_t copycode = copy_length_code(l);
+        const uint32_t cmdcode = combine_length_codes(inscode, copycode, j == 0);
+        const int64_t cost = (cmdcode < 128 ? base_cost : dist_cost) + ((int64_t)copy_extra(copycode) << HQ_QBITS) + M.cost_cmd[cmdcode];
+        if (cost < (int64_t)nodes[pos + l].u) {
+          hq_update_node(nodes, pos, start, l, l, backward, (uint32_t)j + 1, (uint32_t)cost);
+          result = bmax(result, l);
+        }
+        best_len = l;
+      }
+    }
+    if (k >= 2) continue;
+    uint32_t len = min_len;
+    for (uint32_t j = 0; j < num_matches; ++j) {
+      const HqMatch& m = matches[j];
+      const bool is_dict = hqm_is_dict(m);
+      const uint32_t dist = is_dict ? max_distance + 1u + m.dist : m.dist;
+      if (!is_dict && dist > max_distance) continue;  // (cannot happen: the match stage applies the same window limit)
+      uint32_t max_match_len = bmin(hqm_len(m), max_len);
+      if (is_dict && hqm_len(m) > max_len) continue;
+      uint32_t sym_nbits, extra;
+      prefix_encode_copy_distance(dist + 15u, &sym_nbits, &extra);
+      const int64_t dist_cost = base_cost + ((int64_t)(sym_nbits >> 10) << HQ_QBITS) + M.cost_dist[sym_nbits & 0x3ffu];
+      if (len < max_match_len && (is_dict || max_match_len > max_zopfli_len)) len = max_match_len;
+      for (; len <= max_match_len; ++len) {
+        const uint32_t len_code = is_dict ? hqm_len_code(m) : len;
+        const uint32_t copycode = copy_length_code(len_code);
+        const uint32_t cmdcode = combine_length_codes(inscode, copycode, false);
+        const int64_t cost = dist_cost + ((int64_t)copy_extra(copycode) << HQ_QBITS) + M.cost_cmd[cmdcode];
+        if (cost < (int64_t)nodes[pos + len].u) {
+          hq_update_node(nodes, pos, start, len, len_code, dist, 0, (uint32_t)cost);
+          result = bmax(result, len);
+        }
+      }
+    }
+  }
+  return result;
+}
+
+// Parses data[ustart, ustart + len) and writes its commands (copy_len packed as in bro_dict.cuh) to out[]; returns their
+// number, *tail = literals after the last copy, *ncopy = bytes covered by copies.  matches / nmatch are indexed by
+// range-relative position.
+// stats (optional, [256 + 704 + 64], zeroed by the caller): literal / command / distance-symbol histograms of the commands, as the
+// second pass of quality 11 wants them (set_from_commands, hq.rs:1076-1154).
+BRO_HD_NOINLINE uint32_t hq_zopfli_unit(const HqUnit& U, const HqMatch* matches, const uint8_t* nmatch, RawCmd* out, uint32_t* tail,
+                                       uint32_t* ncopy, uint32_t* stats) {
+  ZNode* nodes = U.nodes;
+  const uint32_t len = U.len;
+  const uint32_t max_zopfli_len = hq_max_zopfli_len(U.quality);
+  for (uint32_t i = 0; i <= len; ++i) { nodes[i].length = 1; nodes[i].distance = 0; nodes[i].dcode_insert_length = 0; nodes[i].u = HQ_INF; }
+  nodes[0].length = 0;
+  nodes[0].u = 0;
+  HqQueue Q;
+  Q.idx = 0;
+  for (uint32_t i = 0; i + 3 < len; ++i) {  // ZopfliIterate, hq.rs:1157-1235
+    const uint32_t p = U.ustart + i;
+    const HqMatch* mp = matches + (size_t)p * HQ_MAXM;
+    uint32_t nm = nmatch[p];
+    HqMatch longm;
+    if (nm > 0) {
+      // a match that reached the cap of the match stage is extended to its true length here (the match stage leaves that
+      // to the one position that really takes the copy)
+      longm = mp[nm - 1];
+      if (!hqm_is_dict(longm) && hqm_len(longm) >= HQ_LCAP && len - i > HQ_LCAP) {
+        const uint8_t* cur = U.data + p;
+        const uint32_t full = HQ_LCAP + hq_lcp(cur - longm.dist + HQ_LCAP, cur + HQ_LCAP, len - i - HQ_LCAP);
+        longm.lc = bmin(full, 0xFFFFu);
+      }
+      if (bmin(hqm_len(longm), len - i) > max_zopfli_len) { mp = &longm; nm = 1; }  // hq.rs:917-921
+    }
+    uint32_t skip = hq_update_nodes(U, i, mp, nm, Q);
+    if (skip < 16384) skip = 0;
+    if (nm == 1 && bmin(hqm_len(mp[0]), len - i) > max_zopfli_len) skip = bmax(bmin(hqm_len(mp[0]), len - i), skip);
+    if (skip > 1) {
+      --skip;
+      while (skip) {
+        ++i;
+        if (i + 3 >= len) break;
+        hq_evaluate_node(U, i, Q);
+        --skip;
+      }
+    }
+  }
+  // ComputeShortestPathFromNodes, hq.rs:837-854
+  uint32_t index = len, ncmd = 0;
+  while (zn_insert_length(nodes[index]) == 0 && nodes[index].length == 1 && index > 0) --index;
+  nodes[index].u = 0xFFFFFFFFu;
+  while (index != 0) {
+    const uint32_t l = zn_copy_length(nodes[index]) + zn_insert_length(nodes[index]);
+    index -= l;
+    nodes[index].u = l;
+    ++ncmd;
+  }
+  // BrotliZopfliCreateCommands, hq.rs:97-157 (codes are assigned later by the finalise stage)
+  uint32_t pos = 0, offset = nodes[0].u, k = 0, copied = 0;
+  while (offset != 0xFFFFFFFFu) {
+    const ZNode& next = nodes[pos + offset];
+    const uint32_t clen = zn_copy_length(next), ilen = zn_insert_length(next);
+    pos += ilen;
+    offset = next.u;
+    const uint32_t max_distance = hq_max_distance(U, pos);
+    const bool is_dict = next.distance > max_distance;
+    out[k].insert_len = ilen;
+    out[k].copy_len = is_dict ? pack_dict_len(clen, zn_length_code(next)) : clen;
+    out[k].distance = next.distance;
+    ++k;
+    if (stats) {
+      uint32_t sym_nbits, extra;
+      const uint32_t dcode = zn_distance_code(next);
+      prefix_encode_copy_distance(dcode, &sym_nbits, &extra);
+      const uint32_t cmdcode = combine_length_codes(insert_length_code(ilen), copy_length_code(zn_length_code(next)), dcode == 0);
+      ++stats[256 + cmdcode];
+      if (cmdcode >= 128) ++stats[256 + 704 + (sym_nbits & 0x3ffu)];
+      for (uint32_t j = 0; j < ilen; ++j) ++stats[U.data[U.ustart + pos - ilen + j]];
+    }
+    pos += clen;
+    copied += clen;
+  }
+  *tail = len - pos;
+  *ncopy = copied;
+  return k;
+}
+
+}  // namespace bro

@@ -22,6 +22,7 @@
 #include "bro_meta.cuh"
 #include "bro_parse.cuh"
 #include "bro_split.cuh"
+#include "bro_hq.cuh"
 
 namespace bro {
 
@@ -60,6 +61,8 @@ struct Workspace {
   uint32_t num_units, num_mb;
   // match
   uint32_t* best;
+  HqMatch* hqm;         // quality >= 10: [n][HQ_MAXM] all matches per position (range-relative index)
+  uint8_t* hqn;         //                [n] number of matches
   // parse
   RawCmd* raw;
   uint32_t *unit_ncmd, *unit_tail, *unit_ncopy;
@@ -100,7 +103,11 @@ struct Workspace {
   uint32_t* tree_nbits;   // [num_mb][tree_cap]
   uint8_t* sect_bits;     // [num_mb][HDR_SECTIONS][SECT_BYTES] header sections built beside the trees
   uint32_t* sect_nbits;   // [num_mb][HDR_SECTIONS]
-  uint32_t* ctxmap_ws;    // [num_mb][max_lit_types * 64]
+  uint32_t* ctxmap_ws;    // [num_mb][max_lit_types * 64 + 1024]
+  // quality >= 10: clustered context maps of the metablocks (bro_kernels_hq.cuh fills them)
+  uint8_t* lit_cmap;      // [num_mb][256 * 64] literal (block type, context) -> prefix code
+  uint8_t* dist_cmap;     // [num_mb][256 * 4]
+  uint32_t* cm_counts;    // [num_mb][2] number of literal / distance prefix codes
   // output
   uint32_t* out;          // zero-initialised words
   uint64_t out_cap_bytes;
@@ -131,6 +138,9 @@ __device__ __forceinline__ MetaCodes make_codes(const Workspace& W, uint32_t m) 
   mc.dist_depth = W.dist_depth + (size_t)m * W.max_dist_types * 64; mc.dist_code = W.dist_code + (size_t)m * W.max_dist_types * 64;
   mc.ctx_map_id = W.mb[m].ctx_map_id;
   mc.nctx = ctxmap_num_contexts(mc.ctx_map_id);
+  const bool full = mc.ctx_map_id >= CTXMAP_FULL_UTF8;  // quality >= 10: clustered context maps
+  mc.lit_cmap = full ? W.lit_cmap + (size_t)m * 256 * 64 : nullptr;
+  mc.dist_cmap = full ? W.dist_cmap + (size_t)m * 256 * 4 : nullptr;
   return mc;
 }
 
@@ -1556,7 +1566,7 @@ __global__ void __launch_bounds__(256) k_symbols_long(Workspace W) {
     for (uint32_t off = k * LONG_INS + threadIdx.x; off < min(g.insert_len, (k + 1) * LONG_INS); off += 256) {
       const uint32_t pos = g.pos + off;
       const uint8_t p1 = ((uint64_t)W.P.abs_base + pos >= 1) ? d[(int64_t)pos - 1] : 0, p2 = ((uint64_t)W.P.abs_base + pos >= 2) ? d[(int64_t)pos - 2] : 0;
-      const uint32_t cx = id ? ctxmap_lookup(id, context_utf8(p1, p2)) : 0u;
+      const uint32_t cx = (id && !(id >= CTXMAP_FULL_UTF8 && !W.P.ctx_model)) ? ctxmap_lookup(id, literal_context(id, p1, p2)) : 0u;
       ls[off] = (uint16_t)(d[pos] | (cx << 8));
     }
   });
@@ -1590,6 +1600,10 @@ __global__ void __launch_bounds__(256) k_ctx_decide(Workspace W) {
   for (uint32_t i = threadIdx.x; i < sizeof(CtxSampleHist) / 4; i += blockDim.x) raw[i] = 0;
   __syncthreads();
   const EncParams& P = W.P;
+  if (P.quality >= 10 && P.hq_split) {  // ChooseContextMode (encode.rs:1357-1377), decided on the first 64 KiB
+    if (threadIdx.x == 0) mb.ctx_map_id = hq_is_mostly_utf8(W.data + mb.start, bmin(mb.len, 65536u)) ? CTXMAP_FULL_UTF8 : CTXMAP_FULL_SIGNED;
+    return;
+  }
   if (!P.ctx_model || P.quality < 5 || mb.len < 64) {
     if (threadIdx.x == 0) mb.ctx_map_id = CTXMAP_NONE;
     return;
@@ -1634,10 +1648,12 @@ __global__ void __launch_bounds__(256) k_symbols(Workspace W) {
   if (i >= mb.ncmd) return;
   const GCmd c = W.cmds[(size_t)m * W.cmd_cap + i];
   W.cmd_syms[(size_t)m * W.cmd_cap + i] = c.cmd_prefix;
-  if (c.copy_len != 0 && c.cmd_prefix >= 128) W.dist_syms[(size_t)m * W.cmd_cap + c.dist_idx + W.unit_dist_off[c.pad]] = c.dist_prefix & 0x3ffu;
+  const int id = mb.ctx_map_id;
+  if (c.copy_len != 0 && c.cmd_prefix >= 128)  // quality >= 10: the distance context rides in bits 10..11
+    W.dist_syms[(size_t)m * W.cmd_cap + c.dist_idx + W.unit_dist_off[c.pad]] =
+        (uint16_t)((c.dist_prefix & 0x3ffu) | (id >= CTXMAP_FULL_UTF8 ? distance_context(c.cmd_prefix) << 10 : 0u));
   const uint8_t* d = W.data;
   uint16_t* ls = W.lit_syms + mb.start + c.lit_idx;
-  const int id = mb.ctx_map_id;
   if (c.insert_len > LONG_INS) {  // finished by k_symbols_long
     W.long_tab[(size_t)m * W.long_cap + (c.pos - mb.start) / LONG_INS].x = i + 1;
     W.mb[m].has_long = 1;
@@ -1646,7 +1662,7 @@ __global__ void __launch_bounds__(256) k_symbols(Workspace W) {
   uint8_t p1 = ((uint64_t)W.P.abs_base + c.pos >= 1) ? d[(int64_t)c.pos - 1] : 0, p2 = ((uint64_t)W.P.abs_base + c.pos >= 2) ? d[(int64_t)c.pos - 2] : 0;
   for (uint32_t j = 0; j < c.insert_len; ++j) {
     uint8_t lit = d[c.pos + j];
-    uint32_t cx = id ? ctxmap_lookup(id, context_utf8(p1, p2)) : 0u;
+    uint32_t cx = (id && !(id >= CTXMAP_FULL_UTF8 && !W.P.ctx_model)) ? ctxmap_lookup(id, literal_context(id, p1, p2)) : 0u;
     ls[j] = (uint16_t)(lit | (cx << 8));
     p2 = p1;
     p1 = lit;
@@ -1876,7 +1892,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split_greedy(Workspace W) {
 // header sections that depend only on the block splits are serialised by extra blocks of k_trees, concurrently with
 // the prefix codes: 0..2 block-split codes (literal, command, distance), 3 literal context map, 4 distance context map
 #define HDR_SECTIONS 5
-#define SECT_BYTES 32768  // worst case: 8192 context-map symbols of <= 21 bits + their prefix code
+#define SECT_BYTES 65536  // worst case: 16384 context-map symbols of <= 21 bits + their prefix code
 
 // Warp-cooperative huff_create_tree(): the (count asc, symbol desc) order is a total order, so any correct sort gives
 // the reference's node order -- here a bitonic sort of 64-bit keys in shared memory by all 32 lanes; the two-queue
@@ -1957,7 +1973,8 @@ __global__ void __launch_bounds__(32) k_trees(Workspace W) {
   const EncParams& P = W.P;
   const uint32_t nctx = ctxmap_num_contexts(mb.ctx_map_id);
   const uint32_t* cnt = W.split_counts + (size_t)m * 6;
-  const uint32_t nlit = cnt[1] * nctx, ncmd = cnt[3], ndist = cnt[5];
+  const bool full = mb.ctx_map_id >= CTXMAP_FULL_UTF8;  // quality >= 10: codes = clusters of the context maps
+  const uint32_t nlit = full ? W.cm_counts[(size_t)m * 2] : cnt[1] * nctx, ncmd = cnt[3], ndist = full ? W.cm_counts[(size_t)m * 2 + 1] : cnt[5];
   uint32_t t = blockIdx.x;
   const uint32_t tree_cap_total = W.max_lit_trees + W.max_cmd_types + W.max_dist_types;
   if (t >= tree_cap_total) {  // header section (serial code, one lane)
@@ -1970,10 +1987,13 @@ __global__ void __launch_bounds__(32) k_trees(Workspace W) {
       SplitView v = make_view(W, m, (int)k);
       store_block_split_code(sw, v, sc + k, &ws_s);
     } else if (k == 3) {
-      if (mb.ctx_map_id == CTXMAP_NONE) store_trivial_context_map(sw, cnt[1], 6, &ws_s);
-      else store_static_literal_context_map(sw, cnt[1], mb.ctx_map_id, W.ctxmap_ws + (size_t)m * 256 * 64, &ws_s);
+      uint32_t* rle = W.ctxmap_ws + (size_t)m * (256 * 64 + 1024);
+      if (full) store_context_map(sw, W.lit_cmap + (size_t)m * 256 * 64, cnt[1] << 6, nlit, rle, &ws_s);
+      else if (mb.ctx_map_id == CTXMAP_NONE) store_trivial_context_map(sw, cnt[1], 6, &ws_s);
+      else store_static_literal_context_map(sw, cnt[1], mb.ctx_map_id, rle, &ws_s);
     } else {
-      store_trivial_context_map(sw, cnt[5], 2, &ws_s);
+      if (full) store_context_map(sw, W.dist_cmap + (size_t)m * 256 * 4, cnt[5] << 2, ndist, W.ctxmap_ws + (size_t)m * (256 * 64 + 1024) + 256 * 64, &ws_s);
+      else store_trivial_context_map(sw, cnt[5], 2, &ws_s);
     }
     sw.flush_partial();
     W.sect_nbits[(size_t)m * HDR_SECTIONS + k] = (uint32_t)sw.bit_pos();
@@ -2078,11 +2098,12 @@ __global__ void __launch_bounds__(32) k_header(Workspace W) {
   for (uint32_t k = 0; k < 3; ++k) append_bits(bw, sect + (size_t)k * SECT_BYTES, snb[k]);  // block-split codes
   bw.put(2, 0);
   bw.put(4, 0);
-  for (uint32_t i = 0; i < lv.num_types; ++i) bw.put(2, 2);
+  for (uint32_t i = 0; i < lv.num_types; ++i) bw.put(2, mb.ctx_map_id == CTXMAP_FULL_SIGNED ? 3 : 2);  // CONTEXT_SIGNED / CONTEXT_UTF8
   append_bits(bw, sect + (size_t)3 * SECT_BYTES, snb[3]);  // literal context map
   append_bits(bw, sect + (size_t)4 * SECT_BYTES, snb[4]);  // distance context map
   const uint32_t tree_cap = W.max_lit_trees + W.max_cmd_types + W.max_dist_types;
-  const uint32_t ntrees = lv.num_types * nctx + cv.num_types + dv.num_types;
+  const bool full = mb.ctx_map_id >= CTXMAP_FULL_UTF8;
+  const uint32_t ntrees = (full ? W.cm_counts[(size_t)m * 2] : lv.num_types * nctx) + cv.num_types + (full ? W.cm_counts[(size_t)m * 2 + 1] : dv.num_types);
   for (uint32_t t = 0; t < ntrees; ++t)
     append_bits(bw, W.tree_bits + ((size_t)m * tree_cap + t) * TREE_SLOT_BYTES, W.tree_nbits[(size_t)m * tree_cap + t]);
   bw.flush_partial();

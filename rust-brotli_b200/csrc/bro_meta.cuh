@@ -170,6 +170,74 @@ BRO_HD_NOINLINE void store_static_literal_context_map(BitWriter& bw, uint32_t nu
   bw.put(1, 1);
 }
 
+// General context map (EncodeContextMap, brotli_bit_stream.rs:1783-1858): cmap[size] -> cluster < num_clusters.
+// rle: workspace of `size` u32.
+BRO_HD_NOINLINE void store_context_map(BitWriter& bw, const uint8_t* cmap, uint32_t size, uint32_t num_clusters, uint32_t* rle,
+                                       HuffStoreWs* ws) {
+  store_var_len_uint8(bw, num_clusters - 1);
+  if (num_clusters == 1) return;
+  {  // move-to-front transform
+    uint8_t mtf[256];
+    for (uint32_t i = 0; i < 256; ++i) mtf[i] = (uint8_t)i;
+    for (uint32_t i = 0; i < size; ++i) {
+      const uint8_t v = cmap[i];
+      uint32_t index = 0;
+      while (mtf[index] != v) ++index;
+      rle[i] = index;
+      for (uint32_t k = index; k != 0; --k) mtf[k] = mtf[k - 1];
+      mtf[0] = v;
+    }
+  }
+  uint32_t max_run_length_prefix = 6, out_size = 0;
+  {  // RunLengthCodeZeros
+    uint32_t max_reps = 0;
+    for (uint32_t i = 0; i < size;) {
+      uint32_t reps = 0;
+      for (; i < size && rle[i] != 0; ++i) {}
+      for (; i < size && rle[i] == 0; ++i) ++reps;
+      max_reps = bmax(reps, max_reps);
+    }
+    uint32_t max_prefix = max_reps > 0 ? log2_floor_nz(max_reps) : 0;
+    max_prefix = bmin(max_prefix, max_run_length_prefix);
+    max_run_length_prefix = max_prefix;
+    for (uint32_t i = 0; i < size;) {
+      if (rle[i] != 0) {
+        rle[out_size++] = rle[i] + max_run_length_prefix;
+        ++i;
+      } else {
+        uint32_t reps = 1;
+        for (uint32_t k = i + 1; k < size && rle[k] == 0; ++k) ++reps;
+        i += reps;
+        while (reps != 0) {
+          if (reps < (2u << max_prefix)) {
+            uint32_t p = log2_floor_nz(reps);
+            rle[out_size++] = p + ((reps - (1u << p)) << 9);
+            break;
+          } else {
+            rle[out_size++] = max_prefix + (((1u << max_prefix) - 1u) << 9);
+            reps -= (2u << max_prefix) - 1u;
+          }
+        }
+      }
+    }
+  }
+  uint32_t histogram[272];
+  uint8_t depths[272];
+  uint16_t bits[272];
+  for (uint32_t i = 0; i < 272; ++i) histogram[i] = 0;
+  for (uint32_t i = 0; i < out_size; ++i) ++histogram[rle[i] & 0x1ff];
+  const bool use_rle = max_run_length_prefix > 0;
+  bw.put(1, use_rle ? 1u : 0u);
+  if (use_rle) bw.put(4, max_run_length_prefix - 1);
+  huff_build_and_store(bw, histogram, num_clusters + max_run_length_prefix, num_clusters + max_run_length_prefix, ws, depths, bits);
+  for (uint32_t i = 0; i < out_size; ++i) {
+    const uint32_t sym = rle[i] & 0x1ff, extra = rle[i] >> 9;
+    bw.put(depths[sym], bits[sym]);
+    if (sym > 0 && sym <= max_run_length_prefix) bw.put(sym, extra);
+  }
+  bw.put(1, 1);  // inverse move-to-front at the decoder
+}
+
 BRO_HD void store_compressed_metablock_header(BitWriter& bw, bool is_last, uint32_t length) {
   bw.put(1, is_last ? 1u : 0u);
   if (is_last) bw.put(1, 0);
@@ -200,7 +268,16 @@ struct MetaCodes {
   const uint16_t* dist_code;
   int ctx_map_id;
   uint32_t nctx;
+  // quality >= 10 (ctx_map_id >= CTXMAP_FULL_UTF8): clustered context maps, entries are prefix-code indices
+  const uint8_t* lit_cmap;    // [lit types][64]
+  const uint8_t* dist_cmap;   // [dist types][4], null = one code per distance block type
 };
+BRO_HD uint32_t literal_tree(const MetaCodes& mc, uint32_t type, uint8_t p1, uint8_t p2) {
+  if (mc.ctx_map_id >= CTXMAP_FULL_UTF8) return mc.lit_cmap[type * 64u + literal_context(mc.ctx_map_id, p1, p2)];
+  uint32_t tree = type * mc.nctx;
+  if (mc.ctx_map_id) tree += ctxmap_lookup(mc.ctx_map_id, context_utf8(p1, p2));
+  return tree;
+}
 
 // largest b with starts[b] <= idx
 BRO_HD uint32_t find_block(const uint32_t* starts, uint32_t num_blocks, uint32_t idx) {
@@ -224,7 +301,7 @@ BRO_HD void emit_one_literal(W& w, const MetaCodes& mc, uint32_t rank, const uin
   uint32_t tree = mc.lit.types[b] * mc.nctx;
   if (mc.ctx_map_id) {
     uint8_t p1 = ((uint64_t)abs_base + pos >= 1) ? data[(int64_t)pos - 1] : 0, p2 = ((uint64_t)abs_base + pos >= 2) ? data[(int64_t)pos - 2] : 0;
-    tree += ctxmap_lookup(mc.ctx_map_id, context_utf8(p1, p2));
+    tree = literal_tree(mc, mc.lit.types[b], p1, p2);
   }
   const uint8_t lit = data[pos];
   w.put(mc.lit_depth[tree * 256 + lit], mc.lit_code[tree * 256 + lit]);
@@ -266,18 +343,17 @@ BRO_HD_NOINLINE void emit_command(W& w, const MetaCodes& mc, const Cmd& c, uint3
       bend = (b + 1 < mc.lit.num_blocks) ? mc.lit.starts[b + 1] : 0xFFFFFFFFu;
       if (b > 0 && mc.lit.starts[b] == lit_idx) put_block_switch(w, mc.lit, *mc.lit_sc, b, false);
     }
-    uint32_t tbase = mc.lit.types[b] * mc.nctx;
+    uint32_t type = mc.lit.types[b];
     uint8_t p1 = ((uint64_t)abs_base + pos >= 1) ? data[(int64_t)pos - 1] : 0, p2 = ((uint64_t)abs_base + pos >= 2) ? data[(int64_t)pos - 2] : 0;
     for (uint32_t j = 0; j < c.insert_len; ++j) {
       if (lit_idx + j == bend) {
         ++b;
         bend = (b + 1 < mc.lit.num_blocks) ? mc.lit.starts[b + 1] : 0xFFFFFFFFu;
         put_block_switch(w, mc.lit, *mc.lit_sc, b, false);
-        tbase = mc.lit.types[b] * mc.nctx;
+        type = mc.lit.types[b];
       }
       uint8_t lit = data[pos + j];
-      uint32_t tree = tbase;
-      if (mc.ctx_map_id) tree += ctxmap_lookup(mc.ctx_map_id, context_utf8(p1, p2));
+      const uint32_t tree = literal_tree(mc, type, p1, p2);
       w.put(mc.lit_depth[tree * 256 + lit], mc.lit_code[tree * 256 + lit]);
       p2 = p1;
       p1 = lit;
@@ -290,6 +366,7 @@ BRO_HD_NOINLINE void emit_command(W& w, const MetaCodes& mc, const Cmd& c, uint3
       if (b > 0 && mc.dist.starts[b] == dist_idx) put_block_switch(w, mc.dist, *mc.dist_sc, b, false);
     }
     uint32_t t = mc.dist.types[b];
+    if (mc.dist_cmap) t = mc.dist_cmap[t * 4u + distance_context(c.cmd_prefix)];
     uint32_t sym = c.dist_prefix & 0x3ffu;
     w.put(mc.dist_depth[t * 64 + sym], mc.dist_code[t * 64 + sym]);
     w.put(c.dist_prefix >> 10, c.dist_extra);

@@ -22,7 +22,7 @@ BRO_HD uint32_t chunk_len_at(uint64_t done, uint64_t total) {
 }
 
 struct EncParams {
-  int quality;        // 5..9
+  int quality;        // 5..11
   int lgwin;          // 10..24
   int hash_type;      // 5, 6 or 9 (encode.rs:834-893)
   int key_bits;       // bucket_bits
@@ -40,6 +40,7 @@ struct EncParams {
   int split;          // greedy block splitting on/off
   int ctx_model;      // literal context modelling on/off
   int use_dict;       // static-dictionary matches on/off
+  int hq_split;       // quality >= 10: 1 = BrotliSplitBlock + clustered context maps (default), 0 = the greedy splitter of q5..q9
 };
 
 // ---- scores ----

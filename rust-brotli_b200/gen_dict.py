@@ -52,6 +52,94 @@ def build_hash(data, bits, offs, policy="index"):
     return table
 
 
+# ---- quality 10 / 11: every word (plain, first letter uppercased, all uppercased) by the hash of its first four bytes, and the
+# RFC 7932 appendix B transforms grouped by prefix, so that bro_dict.cuh can enumerate all (word, transform) pairs that match
+# at a position (the job of BrotliFindAllStaticDictionaryMatches, static_dict.rs:309; the reference hard-codes a decision tree
+# over the transforms, here the transform list itself is the table).
+class BrotliTransforms(ctypes.Structure):
+    _fields_ = [("prefix_suffix_size", ctypes.c_uint16), ("prefix_suffix", ctypes.POINTER(ctypes.c_uint8)),
+                ("prefix_suffix_map", ctypes.POINTER(ctypes.c_uint16)), ("num_transforms", ctypes.c_uint32),
+                ("transforms", ctypes.POINTER(ctypes.c_uint8)), ("params", ctypes.POINTER(ctypes.c_uint8)),
+                ("cutoff", ctypes.c_int16 * 10)]
+
+
+def load_transforms():
+    lib = ctypes.CDLL("libbrotlicommon.so.1")
+    lib.BrotliGetTransforms.restype = ctypes.POINTER(BrotliTransforms)
+    t = lib.BrotliGetTransforms().contents
+    ps = bytes(t.prefix_suffix[:t.prefix_suffix_size])
+
+    def s(i):
+        o = t.prefix_suffix_map[i]
+        return ps[o + 1:o + 1 + ps[o]]
+    tr = [(s(t.transforms[3 * i]), t.transforms[3 * i + 1], s(t.transforms[3 * i + 2])) for i in range(t.num_transforms)]
+    assert len(tr) == 121 and tr[0] == (b"", 0, b"") and tr[9] == (b"", 10, b"") and tr[44] == (b"", 11, b"")
+    return tr
+
+
+def to_upper(word, all_):
+    """RFC 7932 section 8: uppercase-first / uppercase-all on (pseudo) UTF-8"""
+    w = bytearray(word)
+    i = 0
+    while i < len(w):
+        c = w[i]
+        if c < 0xC0:
+            if 97 <= c <= 122:
+                w[i] ^= 32
+            step = 1
+        elif c < 0xE0:
+            if i + 1 < len(w):
+                w[i + 1] ^= 32
+            step = 2
+        else:
+            if i + 2 < len(w):
+                w[i + 2] ^= 5
+            step = 3
+        i += step
+        if not all_:
+            break
+    return bytes(w)
+
+
+def build_lut(data, bits, offs):
+    buckets = {}
+    for ln in range(4, 25):
+        for idx in range(1 << bits[ln]):
+            w = data[offs[ln] + ln * idx: offs[ln] + ln * (idx + 1)]
+            seen = {w: 0}
+            first, all_ = to_upper(w, False), to_upper(w, True)
+            if first not in seen:
+                seen[first] = 1
+            if all_ not in seen:
+                seen[all_] = 2
+            for v, kind in seen.items():
+                buckets.setdefault(hash15(v[:4]), []).append((ln, idx, kind))
+    table = [0] * 32768
+    entries = []
+    for h in sorted(buckets):
+        table[h] = len(entries) + 1
+        items = sorted(buckets[h])
+        for k, (ln, idx, kind) in enumerate(items):
+            entries.append(idx | (ln << 16) | (kind << 21) | ((1 << 31) if k + 1 == len(items) else 0))
+    assert len(entries) < 65535
+    return table, entries
+
+
+def hash15(b4):
+    return ((int.from_bytes(b4, "little") * 0x1E35A7BD) & 0xFFFFFFFF) >> 17
+
+
+def build_transform_groups(tr):
+    groups = {}
+    for tid, (pre, typ, suf) in enumerate(tr):
+        if typ >= 12:   # omit-first-N: not searched (the reference does not either)
+            continue
+        assert len(pre) <= 8 and len(suf) <= 8
+        groups.setdefault(pre, []).append((tid, typ, suf))
+    order = sorted(groups, key=lambda p: (len(p), p))
+    return [(p, groups[p]) for p in order]
+
+
 def main(policy="index"):
     data, bits, offs = load_dictionary()
     table = build_hash(data, bits, offs, policy)
@@ -64,6 +152,26 @@ def main(policy="index"):
         for i in range(0, 32768, 16):
             f.write(",".join(str(v) for v in table[i:i + 16]) + ",\n")
         f.write("};\n")
+        lut, entries = build_lut(data, bits, offs)
+        f.write("static const unsigned short kDictLutBuckets[32768] = {\n")
+        for i in range(0, 32768, 16):
+            f.write(",".join(str(v) for v in lut[i:i + 16]) + ",\n")
+        f.write("};\nstatic const unsigned int kDictLutEntries[%d] = {\n" % len(entries))
+        for i in range(0, len(entries), 8):
+            f.write(",".join("%uu" % v for v in entries[i:i + 8]) + ",\n")
+        f.write("};\n")
+        groups = build_transform_groups(load_transforms())
+        # group table: prefix_len, prefix[8], first, count ; transform table: id, type, suffix_len, suffix[8]
+        f.write("static const unsigned char kDictTrGroups[%d][11] = {\n" % len(groups))
+        first = 0
+        for pre, lst in groups:
+            f.write("{%d,%s,%d,%d},\n" % (len(pre), ",".join(str(b) for b in pre.ljust(8, b"\0")), first, len(lst)))
+            first += len(lst)
+        f.write("};\nstatic const unsigned char kDictTransforms[%d][11] = {\n" % first)
+        for pre, lst in groups:
+            for tid, typ, suf in lst:
+                f.write("{%d,%d,%d,%s},\n" % (tid, typ, len(suf), ",".join(str(b) for b in suf.ljust(8, b"\0"))))
+        f.write("};\n#define BRO_DICT_NUM_TR_GROUPS %d\n#define BRO_DICT_NUM_TR %d\n#define BRO_DICT_NUM_LUT_ENTRIES %d\n" % (len(groups), first, len(entries)))
     return OUT
 
 

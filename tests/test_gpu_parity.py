@@ -42,6 +42,50 @@ def test_config1_alice29_q5_w20(encoder, oracle):
     assert len(c) <= len(sys_compress(d, 5, 20)) * 1.005
 
 
+def test_product_against_reference_held_pins(encoder):
+    """The reference's own size vectors for this quality range, asserted on the PRODUCT (not on the oracle):
+    alice29.txt q9 lgwin16 one-shot = 51 737 B exactly (src/enc/encode.rs:3073-3091) -> within +-0.5 %."""
+    d = golden_bytes("alice29.txt")
+    c = encoder.compress(d, 9, 16)
+    assert sys_decompress(c, len(d)) == d
+    assert abs(len(c) - 51737) <= 51737 * 0.005, len(c)
+
+
+def test_custom_dictionary_and_abi_details():
+    """BrotliEncoderSetCustomDictionary (src/ffi/compressor.rs:162): the dictionary becomes window content in front of the
+    stream -- the stream only decodes with the same dictionary attached; total_out is the cumulative count."""
+    import ctypes
+    import rust_brotli_b200 as rb
+    L = rb._capi()
+    d = golden_bytes("alice29.txt")
+    dictionary, payload = d[:60000], d[50000:120000]
+    outs = []
+    for use_dict in (False, True):
+        h = L.BrotliEncoderCreateInstance(None, None, None)
+        assert h
+        assert L.BrotliEncoderSetParameter(h, rb.BROTLI_PARAM_QUALITY, 5)
+        assert not L.BrotliEncoderSetParameter(h, rb.BROTLI_PARAM_CATABLE, 1)  # refused, not ignored
+        assert not L.BrotliEncoderSetParameter(h, rb.BROTLI_PARAM_LARGE_WINDOW, 1)
+        if use_dict:
+            L.BrotliEncoderSetCustomDictionary(h, len(dictionary), dictionary)
+        buf = ctypes.create_string_buffer(len(payload) + 4096)
+        avail_in, avail_out = ctypes.c_size_t(len(payload)), ctypes.c_size_t(len(buf))
+        next_in = ctypes.c_void_p(ctypes.cast(ctypes.c_char_p(payload), ctypes.c_void_p).value)
+        next_out = ctypes.c_void_p(ctypes.addressof(buf))
+        total = ctypes.c_size_t(12345)  # garbage in: the call assigns the cumulative total (encode.rs:1591-1593)
+        assert L.BrotliEncoderCompressStream(h, rb.BROTLI_OPERATION_FINISH, ctypes.byref(avail_in), ctypes.byref(next_in),
+                                             ctypes.byref(avail_out), ctypes.byref(next_out), ctypes.byref(total))
+        n = len(buf) - avail_out.value
+        assert total.value == n and L.BrotliEncoderIsFinished(h)
+        outs.append(buf.raw[:n])
+        L.BrotliEncoderDestroyInstance(h)
+    plain, with_dict = outs
+    assert sys_decompress(plain, len(payload)) == payload
+    from oracle.harness import sys_decompress_with_dictionary
+    assert sys_decompress_with_dictionary(with_dict, len(payload), dictionary) == payload
+    assert len(with_dict) < 0.9 * len(plain)  # the first 10 000 bytes of the payload are literally in the dictionary
+
+
 def test_match_stage_equals_model(encoder, model):
     """Per-position best bucket match (distance << 8 | capped length): CUDA sort+match vs the sequential ring model."""
     d = (golden_bytes("random_then_unicode") + golden_bytes("alice29.txt"))[:400000]

@@ -6,7 +6,7 @@ _ROOT = os.path.dirname(_HERE)
 class EncParams(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in ("quality", "lgwin", "hash_type", "key_bits", "hash_len", "depth", "n_last")] + \
                [(n, ctypes.c_uint32) for n in ("lcap", "unit", "mb_units", "max_backward", "n", "abs_base", "size_hint")] + \
-               [(n, ctypes.c_int) for n in ("use_rle_opt", "split", "ctx_model", "use_dict")]
+               [(n, ctypes.c_int) for n in ("use_rle_opt", "split", "ctx_model", "use_dict", "hq_split")]
 
 class ModelStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in ("num_metablocks", "num_raw_metablocks", "num_commands", "num_literals", "header_bits", "body_bits")] + \
@@ -15,7 +15,7 @@ class ModelStats(ctypes.Structure):
 def build_model(force=False):
     so = os.path.join(_HERE, "libgpu_model.so")
     srcs = [os.path.join(_HERE, "gpu_model.cpp")] + [os.path.join(_ROOT, "rust-brotli_b200", "csrc", f) for f in
-            ("bro_common.cuh", "bro_huffman.cuh", "bro_meta.cuh", "bro_parse.cuh", "bro_split.cuh", "bro_dict.cuh", "bro_finalize.cuh")]
+            ("bro_common.cuh", "bro_huffman.cuh", "bro_meta.cuh", "bro_parse.cuh", "bro_split.cuh", "bro_dict.cuh", "bro_finalize.cuh", "bro_hq.cuh", "bro_bsplit.cuh")]
     inc = os.path.join(_ROOT, "rust-brotli_b200", "csrc", "bro_dict_data.inc")
     if not os.path.exists(inc):  # generated file (static dictionary from the system libbrotlicommon + our hash table)
         subprocess.check_call([os.sys.executable, os.path.join(_ROOT, "rust-brotli_b200", "gen_dict.py")])
