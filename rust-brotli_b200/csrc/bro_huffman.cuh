@@ -1,110 +1,153 @@
-// bro_huffman.cuh -- prefix-code construction and serialisation, one histogram per GPU thread.
-// Semantics follow the reference: entropy_encode.rs:27-56,71-116,133-210 (length-limited tree by
-// count clamping), :211-345 (count smoothing for RLE), :347-525 (code-length RLE), :546-575 (canonical
-// codes); brotli_bit_stream.rs:764-911,1401-1498 (serialisation).
+// bro_huffman.cuh -- prefix codes: count smoothing, length-limited code lengths, canonical codes, code description.
+//
+// What the brotli format (RFC 7932 section 3) fixes: canonical code assignment from the lengths, the maximum length (15; 5 for the
+// code-length code), the code-length alphabet (0..15 literal, 16 = repeat the previous non-zero length, 17 = repeat zero, with
+// compounding repeats), the storage order of the code-length code and its fixed variable-length code, and the simple-code form
+// for <= 4 symbols.  Everything else is this encoder's own:
+//   * huff_smooth_counts   -- which counts are flattened so that the lengths run-length code well (the reference's counterpart
+//                             is BrotliOptimizeHuffmanCountsForRle, entropy_encode.rs:211);
+//   * huff_lengths_sorted  -- Huffman code lengths by a two-queue merge over the sorted counts with parent links (depths are
+//                             read off the links), and a Kraft-sum repair when the tree is deeper than the limit (the reference
+//                             rebuilds the tree with clamped counts until it fits, entropy_encode.rs:133-210);
+//   * huff_rle_lengths     -- the run-length form of the length sequence: repeat counts are written in bijective base 4 / 8,
+//                             and a run is split "literal + repeats" exactly when that needs fewer symbols.
+// All routines are sequential (one GPU thread or the CPU model); k_trees replaces the sort by a warp-wide bitonic sort and
+// runs the rest on one lane out of shared memory.
 #pragma once
 #include "bro_common.cuh"
 
 namespace bro {
 
-struct HuffNode {
-  uint32_t count;
-  int16_t left;
-  int16_t right_or_value;
+#define HUFF_MAX_SYMS 704u
+
+struct HuffWs {  // scratch of one code (shared memory in k_trees)
+  uint64_t key[1024];                  // used symbols: count << 16 | symbol, sorted ascending (1024: bitonic padding)
+  uint32_t weight[2 * HUFF_MAX_SYMS];  // leaves in sorted order, then internal nodes in creation order
+  uint16_t parent[2 * HUFF_MAX_SYMS];
+  uint16_t node_depth[2 * HUFF_MAX_SYMS];
+  uint8_t rle_sym[HUFF_MAX_SYMS];      // run-length form of the code lengths
+  uint8_t rle_extra[HUFF_MAX_SYMS];
 };
-// workspace: at least 2 * n + 2 nodes
+typedef HuffWs HuffStoreWs;
 
-BRO_HD bool huff_sort_less(const HuffNode& a, const HuffNode& b) {
-  if (a.count != b.count) return a.count < b.count;
-  return a.right_or_value > b.right_or_value;
-}
-
-BRO_HD_NOINLINE bool huff_set_depth(int p0, HuffNode* pool, uint8_t* depth, int max_depth) {
-  int stack[16];
-  int level = 0;
-  int p = p0;
-  stack[0] = -1;
-  for (;;) {
-    if (pool[p].left >= 0) {
-      level++;
-      if (level > max_depth) return false;
-      stack[level] = pool[p].right_or_value;
-      p = pool[p].left;
-      continue;
-    } else {
-      depth[pool[p].right_or_value] = (uint8_t)level;
+// Count smoothing before the prefix code is built (the job of BrotliOptimizeHuffmanCountsForRle, entropy_encode.rs:211-345: trade a few
+// body bits for a code-length sequence that run-length codes well).  Own formulation, derived from the two costs involved:
+// replacing the counts c_i of a run by their mean m costs about sum (c_i - m)^2 / (2 m ln 2) body bits, and saves about 2..3
+// header bits per symbol once the run is long enough for a repeat code.  So a run (consecutive used symbols) is grown greedily
+// while the next count stays within two standard deviations of the run's mean under a Poisson model, (c - m)^2 <= 4 m + slack
+// (slack = min(16, total / 256): in a large histogram counts below ~10 get an absolute slack of 4), and a run of at least
+// HUFF_SMOOTH_RUN symbols is set to its rounded mean.
+#ifndef HUFF_SMOOTH_RUN
+#define HUFF_SMOOTH_RUN 4u
+#endif
+#ifndef HUFF_SMOOTH_DENSITY_NUM
+#define HUFF_SMOOTH_DENSITY_NUM 1u
+#define HUFF_SMOOTH_DENSITY_DEN 4u
+#endif
+BRO_HD_NOINLINE void huff_smooth_counts(uint32_t length, uint32_t* counts) {
+  uint32_t used = 0;
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < length; ++i) { used += counts[i] != 0; total += counts[i]; }
+  if (used < 16) return;  // small codes are stored with few bits anyway
+  const uint64_t slack = total >> 8 < 16 ? total >> 8 : 16;  // the absolute slack shrinks with the histogram: in a small one every count matters
+  while (length != 0 && counts[length - 1] == 0) --length;  // the unused tail of the alphabet is not coded at all
+  for (uint32_t i = 0; i < length;) {
+    uint64_t sum = counts[i], n = 1, nz = counts[i] != 0;
+    uint32_t j = i + 1;
+    for (; j < length; ++j) {
+      const int64_t dev = (int64_t)counts[j] * (int64_t)n - (int64_t)sum;      // n * (c - mean)
+      if ((uint64_t)(dev * dev) > n * (4 * sum + slack * n)) break;             // (c - m)^2 > 4 m + slack
+      sum += counts[j];
+      nz += counts[j] != 0;
+      ++n;
     }
-    while (level >= 0 && stack[level] == -1) level--;
-    if (level < 0) return true;
-    p = stack[level];
-    stack[level] = -1;
+    // an unused symbol is a count of 0 under the same test, so sparse regions (a few symbols seen once or twice) form runs too;
+    // they are filled only if at least HUFF_SMOOTH_DENSITY of their symbols are in use -- otherwise zero runs code better
+    if (n >= HUFF_SMOOTH_RUN && nz * HUFF_SMOOTH_DENSITY_DEN >= n * HUFF_SMOOTH_DENSITY_NUM) {
+      uint32_t mean = (uint32_t)((sum + n / 2) / n);
+      if (mean == 0) mean = 1;
+      for (uint32_t k = i; k < j; ++k) counts[k] = mean;
+    }
+    i = j;
   }
 }
 
-BRO_HD_NOINLINE void huff_sort(HuffNode* items, uint32_t n) {
-  static constexpr uint32_t gaps[6] = {132, 57, 23, 10, 4, 1};
-  if (n < 13) {
-    for (uint32_t i = 1; i < n; ++i) {
-      HuffNode tmp = items[i];
-      uint32_t k = i, j = i - 1;
-      while (huff_sort_less(tmp, items[j])) {
-        items[k] = items[j];
-        k = j;
-        if (!j--) break;
-      }
-      items[k] = tmp;
-    }
-  } else {
-    for (int g = n < 57 ? 2 : 0; g < 6; ++g) {
-      uint32_t gap = gaps[g];
-      for (uint32_t i = gap; i < n; ++i) {
-        uint32_t j = i;
-        HuffNode tmp = items[i];
-        for (; j >= gap && huff_sort_less(tmp, items[j - gap]); j -= gap) items[j] = items[j - gap];
-        items[j] = tmp;
-      }
+// used symbols as sort keys (count << 16 | symbol); returns their number
+BRO_HD uint32_t huff_collect_keys(const uint32_t* counts, uint32_t length, uint64_t* key) {
+  uint32_t n = 0;
+  for (uint32_t i = 0; i < length; ++i) if (counts[i]) key[n++] = ((uint64_t)counts[i] << 16) | i;
+  return n;
+}
+BRO_HD_NOINLINE void huff_sort_keys(uint64_t* key, uint32_t n) {  // ascending; shell sort with the 3x+1 gap sequence
+  uint32_t gap = 1;
+  while (gap < n / 3) gap = 3 * gap + 1;
+  for (; gap >= 1; gap /= 3) {
+    for (uint32_t i = gap; i < n; ++i) {
+      const uint64_t v = key[i];
+      uint32_t j = i;
+      for (; j >= gap && key[j - gap] > v; j -= gap) key[j] = key[j - gap];
+      key[j] = v;
     }
   }
 }
-
-// depth[] must be zero for unused symbols on entry (it is only written for used ones).
-BRO_HD_NOINLINE void huff_create_tree(const uint32_t* data, uint32_t length, int tree_limit, HuffNode* tree,
-                                      uint8_t* depth) {
-  HuffNode sentinel;
-  sentinel.count = 0xFFFFFFFFu;
-  sentinel.left = -1;
-  sentinel.right_or_value = -1;
-  for (uint32_t count_limit = 1;; count_limit *= 2) {
-    uint32_t n = 0;
-    for (uint32_t i = length; i != 0;) {
-      --i;
-      if (data[i]) {
-        tree[n].count = bmax(data[i], count_limit);
-        tree[n].left = -1;
-        tree[n].right_or_value = (int16_t)i;
-        ++n;
+// Code lengths of the n >= 2 symbols in ws->key (sorted ascending), at most `limit` bits; depth[] is written for those symbols
+// only.
+BRO_HD_NOINLINE void huff_lengths_sorted(HuffWs* ws, uint32_t n, uint32_t limit, uint8_t* depth) {
+  uint32_t* weight = ws->weight;
+  uint16_t* parent = ws->parent;
+  uint16_t* nd = ws->node_depth;
+  for (uint32_t i = 0; i < n; ++i) weight[i] = (uint32_t)(ws->key[i] >> 16);
+  // two-queue merge: leaves 0..n-1 ascending, internal nodes n..2n-2 are created in non-decreasing weight order, so the two
+  // smallest nodes are always at the heads of the two queues (a leaf wins a tie: shallower trees)
+  uint32_t leaf = 0, inner = n, next = n;
+  for (uint32_t k = 0; k + 1 < n; ++k) {
+    uint32_t pick[2];
+    for (int t = 0; t < 2; ++t) {
+      if (leaf < n && (inner >= next || weight[leaf] <= weight[inner])) pick[t] = leaf++;
+      else pick[t] = inner++;
+    }
+    weight[next] = weight[pick[0]] + weight[pick[1]];
+    parent[pick[0]] = (uint16_t)next;
+    parent[pick[1]] = (uint16_t)next;
+    ++next;
+  }
+  const uint32_t root = next - 1;
+  nd[root] = 0;
+  uint32_t maxd = 0;
+  for (uint32_t v = root; v-- > 0;) {  // a parent is always created after its children: one backward sweep
+    nd[v] = (uint16_t)(nd[parent[v]] + 1);
+    if (v < n && nd[v] > maxd) maxd = nd[v];
+  }
+  if (maxd > limit) {
+    // Kraft-sum repair.  Clamp to the limit, then lengthen the least frequent symbols that still have room until the code is
+    // feasible again (each extra bit on a symbol of length l frees 2^(limit - l - 1) units of 2^-limit), then hand any slack
+    // back to the most frequent symbols that can use it.
+    int64_t excess = -((int64_t)1 << limit);
+    for (uint32_t i = 0; i < n; ++i) {
+      if (nd[i] > limit) nd[i] = (uint16_t)limit;
+      excess += (int64_t)1 << (limit - nd[i]);
+    }
+    for (uint32_t i = 0; excess > 0 && i < n;) {
+      if (nd[i] >= limit) { ++i; continue; }
+      excess -= (int64_t)1 << (limit - nd[i] - 1);
+      ++nd[i];
+    }
+    for (uint32_t i = n; i-- > 0 && excess < 0;) {
+      while (nd[i] > 1 && ((int64_t)1 << (limit - nd[i])) <= -excess && (i + 1 == n || nd[i] - 1 >= nd[i + 1])) {
+        excess += (int64_t)1 << (limit - nd[i]);
+        --nd[i];
       }
     }
-    if (n == 1) {
-      depth[tree[0].right_or_value] = 1;
-      return;
-    }
-    huff_sort(tree, n);
-    tree[n] = sentinel;
-    tree[n + 1] = sentinel;
-    uint32_t i = 0, j = n + 1;
-    for (uint32_t k = n - 1; k != 0; --k) {
-      uint32_t left, right;
-      if (tree[i].count <= tree[j].count) left = i++; else left = j++;
-      if (tree[i].count <= tree[j].count) right = i++; else right = j++;
-      uint32_t j_end = 2 * n - k;
-      tree[j_end].count = tree[left].count + tree[right].count;
-      tree[j_end].left = (int16_t)left;
-      tree[j_end].right_or_value = (int16_t)right;
-      tree[j_end + 1] = sentinel;
-    }
-    if (huff_set_depth((int)(2 * n - 1), tree, depth, tree_limit)) return;
   }
+  for (uint32_t i = 0; i < n; ++i) depth[ws->key[i] & 0xFFFFu] = (uint8_t)nd[i];
+}
+// Code lengths of a histogram.  depth[] must be zero on entry (it is written for used symbols only).
+BRO_HD_NOINLINE void huff_code_lengths(const uint32_t* counts, uint32_t length, uint32_t limit, HuffWs* ws, uint8_t* depth) {
+  const uint32_t n = huff_collect_keys(counts, length, ws->key);
+  if (n == 0) return;
+  if (n == 1) { depth[ws->key[0] & 0xFFFFu] = 1; return; }
+  huff_sort_keys(ws->key, n);
+  huff_lengths_sorted(ws, n, limit, depth);
 }
 
 BRO_HD uint16_t reverse_bits(uint32_t num_bits, uint32_t bits) {
@@ -118,248 +161,137 @@ BRO_HD uint16_t reverse_bits(uint32_t num_bits, uint32_t bits) {
   }
   return (uint16_t)r;
 }
+// canonical codes (RFC 7932 section 3.2), bit-reversed because the stream is written LSB first
 BRO_HD_NOINLINE void huff_depths_to_codes(const uint8_t* depth, uint32_t len, uint16_t* codes) {
-  uint16_t bl_count[16], next_code[16];
-  for (int i = 0; i < 16; ++i) bl_count[i] = 0;
-  for (uint32_t i = 0; i < len; ++i) bl_count[depth[i]]++;
-  bl_count[0] = 0;
-  next_code[0] = 0;
-  int code = 0;
-  for (int i = 1; i < 16; ++i) {
-    code = (code + bl_count[i - 1]) << 1;
-    next_code[i] = (uint16_t)code;
+  uint32_t per_len[16], next_code[16];
+  for (int l = 0; l < 16; ++l) per_len[l] = 0;
+  for (uint32_t i = 0; i < len; ++i) ++per_len[depth[i]];
+  uint32_t code = 0;
+  per_len[0] = 0;
+  for (int l = 1; l < 16; ++l) {
+    code = (code + per_len[l - 1]) << 1;
+    next_code[l] = code;
   }
-  for (uint32_t i = 0; i < len; ++i)
-    if (depth[i]) codes[i] = reverse_bits(depth[i], next_code[depth[i]]++);
-}
-
-// entropy_encode.rs:211-345; good_for_rle: workspace of `length` bytes
-BRO_HD_NOINLINE void huff_optimize_counts_for_rle(uint32_t length, uint32_t* counts, uint8_t* good_for_rle) {
-  uint32_t nonzero_count = 0;
-  const uint32_t streak_limit = 1240;
-  for (uint32_t i = 0; i < length; ++i) if (counts[i]) ++nonzero_count;
-  if (nonzero_count < 16) return;
-  while (length != 0 && counts[length - 1] == 0) --length;
-  if (length == 0) return;
-  {
-    uint32_t nonzeros = 0, smallest_nonzero = 1u << 30;
-    for (uint32_t i = 0; i < length; ++i) {
-      if (counts[i] != 0) {
-        ++nonzeros;
-        if (smallest_nonzero > counts[i]) smallest_nonzero = counts[i];
-      }
-    }
-    if (nonzeros < 5) return;
-    if (smallest_nonzero < 4) {
-      uint32_t zeros = length - nonzeros;
-      if (zeros < 6)
-        for (uint32_t i = 1; i + 1 < length; ++i)
-          if (counts[i - 1] != 0 && counts[i] == 0 && counts[i + 1] != 0) counts[i] = 1;
-    }
-    if (nonzeros < 28) return;
-  }
-  for (uint32_t i = 0; i < length; ++i) good_for_rle[i] = 0;
-  {
-    uint32_t symbol = counts[0];
-    uint32_t step = 0;
-    for (uint32_t i = 0; i <= length; ++i) {
-      if (i == length || counts[i] != symbol) {
-        if ((symbol == 0 && step >= 5) || (symbol != 0 && step >= 7))
-          for (uint32_t k = 0; k < step; ++k) good_for_rle[i - k - 1] = 1;
-        step = 1;
-        if (i != length) symbol = counts[i];
-      } else {
-        ++step;
-      }
-    }
-  }
-  uint64_t stride = 0, sum = 0;
-  uint64_t limit = 256ull * ((uint64_t)counts[0] + counts[1] + counts[2]) / 3 + 420;
-  for (uint32_t i = 0; i <= length; ++i) {
-    bool brk = (i == length) || good_for_rle[i] || (i != 0 && good_for_rle[i - 1]);
-    if (!brk) brk = (256ull * counts[i] - limit + streak_limit) >= 2ull * streak_limit;  // unsigned wrap intended
-    if (brk) {
-      if (stride >= 4 || (stride >= 3 && sum == 0)) {
-        uint64_t count = (sum + stride / 2) / stride;
-        if (count == 0) count = 1;
-        if (sum == 0) count = 0;
-        for (uint32_t k = 0; k < stride; ++k) counts[i - k - 1] = (uint32_t)count;
-      }
-      stride = 0;
-      sum = 0;
-      if (i + 2 < length) limit = 256ull * ((uint64_t)counts[i] + counts[i + 1] + counts[i + 2]) / 3 + 420;
-      else if (i < length) limit = 256ull * counts[i];
-      else limit = 0;
-    }
-    ++stride;
-    if (i != length) {
-      sum += counts[i];
-      if (stride >= 4) limit = (256ull * sum + stride / 2) / stride;
-      if (stride == 4) limit += 120;
-    }
+  for (uint32_t i = 0; i < len; ++i) {
+    const uint32_t l = depth[i];
+    if (l) codes[i] = reverse_bits(l, next_code[l]++);
   }
 }
 
-// ---- code-length RLE (entropy_encode.rs:347-525) ----
-BRO_HD void cl_reverse(uint8_t* v, uint32_t start, uint32_t end) {
-  --end;
-  while (start < end) {
-    uint8_t t = v[start];
-    v[start] = v[end];
-    v[end] = t;
-    ++start;
-    --end;
+// ---- run-length form of a code length sequence ----
+// A run of r repeats written with k compounding repeat symbols covers r - 2 = sum d_j B^(k-j) with digits d_j in 1..B (B = 4 for
+// symbol 16, 8 for symbol 17): bijective base-B numeration; the extra bits of a symbol are d_j - 1.
+BRO_HD uint32_t huff_repeat_symbols(uint32_t r, uint32_t B) {  // symbols needed for r >= 3 repeats
+  uint32_t k = 0;
+  for (uint32_t x = r - 2; x > 0; x = (x - 1) / B) ++k;  // (x - d) / B with d = ((x - 1) % B) + 1
+  return k;
+}
+BRO_HD void huff_put_repeats(uint32_t r, uint32_t B, uint8_t symbol, uint32_t* n, uint8_t* sym, uint8_t* extra) {
+  const uint32_t k = huff_repeat_symbols(r, B);
+  uint32_t x = r - 2;
+  for (uint32_t j = k; j-- > 0;) {  // least significant digit is written last
+    const uint32_t d = ((x - 1) % B) + 1;
+    sym[*n + j] = symbol;
+    extra[*n + j] = (uint8_t)(d - 1);
+    x = (x - d) / B;
+  }
+  *n += k;
+}
+// Emits `r` further occurrences of the current value (the repeat symbol repeats `value`): as literals when that is not longer,
+// else as one compound repeat, or as a literal followed by a compound repeat of r - 1 when the shorter run needs one symbol less.
+BRO_HD void huff_put_run(uint8_t value, uint32_t r, uint32_t* n, uint8_t* sym, uint8_t* extra) {
+  const uint32_t B = value ? 4u : 8u;
+  const uint8_t rep = value ? 16 : 17;
+  while (r > 0) {
+    if (r < 3) { sym[*n] = value; extra[*n] = 0; ++*n; --r; continue; }
+    if (r > 3 && huff_repeat_symbols(r - 1, B) < huff_repeat_symbols(r, B)) { sym[*n] = value; extra[*n] = 0; ++*n; --r; }
+    huff_put_repeats(r, B, rep, n, sym, extra);
+    r = 0;
   }
 }
-BRO_HD_NOINLINE void cl_write_reps(uint8_t prev, uint8_t value, uint32_t reps, uint32_t* n, uint8_t* tree, uint8_t* extra) {
-  if (prev != value) { tree[*n] = value; extra[*n] = 0; ++*n; --reps; }
-  if (reps == 7) { tree[*n] = value; extra[*n] = 0; ++*n; --reps; }
-  if (reps < 3) {
-    for (uint32_t i = 0; i < reps; ++i) { tree[*n] = value; extra[*n] = 0; ++*n; }
-  } else {
-    uint32_t start = *n;
-    reps -= 3;
-    for (;;) {
-      tree[*n] = 16; extra[*n] = (uint8_t)(reps & 3); ++*n;
-      reps >>= 2;
-      if (reps == 0) break;
-      --reps;
+BRO_HD_NOINLINE uint32_t huff_rle_lengths(const uint8_t* depth, uint32_t length, uint8_t* sym, uint8_t* extra) {
+  while (length > 0 && depth[length - 1] == 0) --length;  // trailing unused symbols are implied
+  uint32_t n = 0;
+  uint8_t prev_nonzero = 8;  // the format's initial "previous length"
+  for (uint32_t i = 0; i < length;) {
+    const uint8_t v = depth[i];
+    uint32_t r = 1;
+    while (i + r < length && depth[i + r] == v) ++r;
+    i += r;
+    if (v != 0 && v != prev_nonzero) {  // a repeat symbol repeats the last non-zero length: a new value needs one literal first
+      sym[n] = v; extra[n] = 0; ++n;
+      --r;
+      prev_nonzero = v;
     }
-    cl_reverse(tree, start, *n);
-    cl_reverse(extra, start, *n);
+    huff_put_run(v, r, &n, sym, extra);
   }
-}
-BRO_HD_NOINLINE void cl_write_zero_reps(uint32_t reps, uint32_t* n, uint8_t* tree, uint8_t* extra) {
-  if (reps == 11) { tree[*n] = 0; extra[*n] = 0; ++*n; --reps; }
-  if (reps < 3) {
-    for (uint32_t i = 0; i < reps; ++i) { tree[*n] = 0; extra[*n] = 0; ++*n; }
-  } else {
-    uint32_t start = *n;
-    reps -= 3;
-    for (;;) {
-      tree[*n] = 17; extra[*n] = (uint8_t)(reps & 7); ++*n;
-      reps >>= 3;
-      if (reps == 0) break;
-      --reps;
-    }
-    cl_reverse(tree, start, *n);
-    cl_reverse(extra, start, *n);
-  }
-}
-BRO_HD_NOINLINE void cl_write_tree(const uint8_t* depth, uint32_t length, uint32_t* n, uint8_t* tree, uint8_t* extra) {
-  uint8_t previous_value = 8;
-  bool use_nz = false, use_z = false;
-  uint32_t new_length = length;
-  for (uint32_t i = 0; i < length; ++i) {
-    if (depth[length - i - 1] == 0) --new_length; else break;
-  }
-  if (length > 50) {  // decide_over_rle_use
-    uint32_t total_reps_zero = 0, total_reps_non_zero = 0, count_reps_zero = 1, count_reps_non_zero = 1;
-    for (uint32_t i = 0; i < new_length;) {
-      uint8_t value = depth[i];
-      uint32_t reps = 1;
-      for (uint32_t k = i + 1; k < new_length && depth[k] == value; ++k) ++reps;
-      if (reps >= 3 && value == 0) { total_reps_zero += reps; ++count_reps_zero; }
-      if (reps >= 4 && value != 0) { total_reps_non_zero += reps; ++count_reps_non_zero; }
-      i += reps;
-    }
-    use_nz = total_reps_non_zero > count_reps_non_zero * 2;
-    use_z = total_reps_zero > count_reps_zero * 2;
-  }
-  for (uint32_t i = 0; i < new_length;) {
-    uint8_t value = depth[i];
-    uint32_t reps = 1;
-    if ((value != 0 && use_nz) || (value == 0 && use_z))
-      for (uint32_t k = i + 1; k < new_length && depth[k] == value; ++k) ++reps;
-    if (value == 0) cl_write_zero_reps(reps, n, tree, extra);
-    else { cl_write_reps(previous_value, value, reps, n, tree, extra); previous_value = value; }
-    i += reps;
-  }
+  return n;
 }
 
-// workspace for serialising one code: RLE symbols + extra bits
-struct HuffStoreWs {
-  uint8_t rle[704];
-  uint8_t extra[704];
-  HuffNode nodes[2 * 704 + 2];
-};
-
-BRO_HD_NOINLINE void huff_store_complex(BitWriter& bw, const uint8_t* depths, uint32_t num, HuffStoreWs* ws) {
-  uint32_t tree_size = 0;
+// Complex prefix code description (RFC 7932 section 3.5): the code-length code (lengths in the format's storage order, with
+// its fixed variable-length code), then the run-length coded lengths.
+BRO_HD_NOINLINE void huff_store_complex(BitWriter& bw, const uint8_t* depths, uint32_t num, HuffWs* ws) {
   uint8_t cl_depth[18];
   uint16_t cl_bits[18];
-  uint32_t histogram[18];
-  for (int i = 0; i < 18; ++i) { cl_depth[i] = 0; cl_bits[i] = 0; histogram[i] = 0; }
-  cl_write_tree(depths, num, &tree_size, ws->rle, ws->extra);
-  for (uint32_t i = 0; i < tree_size; ++i) ++histogram[ws->rle[i]];
-  int num_codes = 0;
-  uint32_t code = 0;
-  for (uint32_t i = 0; i < 18; ++i) {
-    if (histogram[i]) {
-      if (num_codes == 0) { code = i; num_codes = 1; }
-      else if (num_codes == 1) { num_codes = 2; break; }
-    }
-  }
-  huff_create_tree(histogram, 18, 5, ws->nodes, cl_depth);
+  uint32_t cl_hist[18];
+  for (int i = 0; i < 18; ++i) { cl_depth[i] = 0; cl_bits[i] = 0; cl_hist[i] = 0; }
+  const uint32_t nsym = huff_rle_lengths(depths, num, ws->rle_sym, ws->rle_extra);
+  for (uint32_t i = 0; i < nsym; ++i) ++cl_hist[ws->rle_sym[i]];
+  uint32_t used = 0, only = 0;
+  for (uint32_t i = 0; i < 18; ++i) if (cl_hist[i]) { if (!used) only = i; ++used; }
+  huff_code_lengths(cl_hist, 18, 5, ws, cl_depth);
   huff_depths_to_codes(cl_depth, 18, cl_bits);
-  {  // brotli_bit_stream.rs:764-808
-    static constexpr uint8_t kStorageOrder[18] = {1, 2, 3, 4, 0, 5, 17, 6, 16, 7, 8, 9, 10, 11, 12, 13, 14, 15};
-    static constexpr uint8_t kSymbols[6] = {0, 7, 3, 2, 1, 15};
-    static constexpr uint8_t kLengths[6] = {2, 4, 3, 2, 2, 4};
-    uint32_t skip_some = 0, codes_to_store = 18;
-    if (num_codes > 1)
-      for (; codes_to_store > 0; --codes_to_store)
-        if (cl_depth[kStorageOrder[codes_to_store - 1]] != 0) break;
-    if (cl_depth[kStorageOrder[0]] == 0 && cl_depth[kStorageOrder[1]] == 0) {
-      skip_some = 2;
-      if (cl_depth[kStorageOrder[2]] == 0) skip_some = 3;
-    }
-    bw.put(2, skip_some);
-    for (uint32_t i = skip_some; i < codes_to_store; ++i) {
-      uint32_t l = cl_depth[kStorageOrder[i]];
-      bw.put(kLengths[l], kSymbols[l]);
+  {
+    static constexpr uint8_t kOrder[18] = {1, 2, 3, 4, 0, 5, 17, 6, 16, 7, 8, 9, 10, 11, 12, 13, 14, 15};  // format: storage order
+    static constexpr uint8_t kVlcBits[6] = {0, 7, 3, 2, 1, 15};                                            // format: fixed code of a length 0..5
+    static constexpr uint8_t kVlcLen[6] = {2, 4, 3, 2, 2, 4};
+    uint32_t last = 18;  // lengths after the last non-zero one are implied
+    if (used > 1) while (last > 0 && cl_depth[kOrder[last - 1]] == 0) --last;
+    uint32_t skip = 0;   // HSKIP: the first two or three (zero) lengths can be skipped
+    if (cl_depth[kOrder[0]] == 0 && cl_depth[kOrder[1]] == 0) skip = cl_depth[kOrder[2]] == 0 ? 3u : 2u;
+    bw.put(2, skip);
+    for (uint32_t i = skip; i < last; ++i) {
+      const uint32_t l = cl_depth[kOrder[i]];
+      bw.put(kVlcLen[l], kVlcBits[l]);
     }
   }
-  if (num_codes == 1) cl_depth[code] = 0;
-  for (uint32_t i = 0; i < tree_size; ++i) {
-    uint32_t s = ws->rle[i];
+  if (used == 1) cl_depth[only] = 0;  // a code with a single symbol takes no bits
+  for (uint32_t i = 0; i < nsym; ++i) {
+    const uint32_t s = ws->rle_sym[i];
     bw.put(cl_depth[s], cl_bits[s]);
-    if (s == 16) bw.put(2, ws->extra[i]);
-    else if (s == 17) bw.put(3, ws->extra[i]);
+    if (s == 16) bw.put(2, ws->rle_extra[i]);
+    else if (s == 17) bw.put(3, ws->rle_extra[i]);
   }
 }
 
-// brotli_bit_stream.rs:1445-1498.  depth/codes arrays have histogram_length entries and are fully written.
+// Builds the code of a histogram (depth / codes get histogram_length entries) and appends its description to bw:
+// 0 or 1 used symbols -> the one-symbol form, <= 4 -> the simple form, else the complex form (RFC 7932 sections 3.4, 3.5).
 BRO_HD_NOINLINE void huff_build_and_store(BitWriter& bw, const uint32_t* histogram, uint32_t histogram_length,
-                                          uint32_t alphabet_size, HuffStoreWs* ws, uint8_t* depth, uint16_t* codes) {
-  uint32_t count = 0, s4[4] = {0, 0, 0, 0}, max_bits = 0;
-  for (uint32_t i = 0; i < histogram_length; ++i) {
-    if (histogram[i]) {
-      if (count < 4) s4[count] = i;
-      else if (count > 4) break;
-      count++;
-    }
-  }
-  for (uint32_t c = alphabet_size - 1; c; c >>= 1) ++max_bits;
+                                          uint32_t alphabet_size, HuffWs* ws, uint8_t* depth, uint16_t* codes) {
+  uint32_t used = 0, first4[4] = {0, 0, 0, 0}, sym_bits = 0;
+  for (uint32_t i = 0; i < histogram_length && used < 5; ++i)
+    if (histogram[i]) { if (used < 4) first4[used] = i; ++used; }
+  for (uint32_t c = alphabet_size - 1; c; c >>= 1) ++sym_bits;
   for (uint32_t i = 0; i < histogram_length; ++i) { depth[i] = 0; codes[i] = 0; }
-  if (count <= 1) {
-    bw.put(4, 1);
-    bw.put(max_bits, s4[0]);
+  if (used <= 1) {
+    bw.put(4, 1);  // simple code, one symbol
+    bw.put(sym_bits, first4[0]);
     return;
   }
-  huff_create_tree(histogram, histogram_length, 15, ws->nodes, depth);
+  huff_code_lengths(histogram, histogram_length, 15, ws, depth);
   huff_depths_to_codes(depth, histogram_length, codes);
-  if (count <= 4) {  // StoreSimpleHuffmanTree brotli_bit_stream.rs:1401-1443
-    bw.put(2, 1);
-    bw.put(2, count - 1);
-    for (uint32_t i = 0; i < count; ++i)
-      for (uint32_t j = i + 1; j < count; ++j)
-        if (depth[s4[j]] < depth[s4[i]]) { uint32_t t = s4[j]; s4[j] = s4[i]; s4[i] = t; }
-    for (uint32_t i = 0; i < count; ++i) bw.put(max_bits, s4[i]);
-    if (count == 4) bw.put(1, depth[s4[0]] == 1 ? 1u : 0u);
-  } else {
-    huff_store_complex(bw, depth, histogram_length, ws);
+  if (used > 4) { huff_store_complex(bw, depth, histogram_length, ws); return; }
+  // simple code: the symbols in order of code length (the lengths themselves are implied by NSYM and the tree-select bit)
+  for (uint32_t i = 1; i < used; ++i) {
+    const uint32_t v = first4[i];
+    uint32_t j = i;
+    for (; j > 0 && depth[first4[j - 1]] > depth[v]; --j) first4[j] = first4[j - 1];
+    first4[j] = v;
   }
+  bw.put(2, 1);
+  bw.put(2, used - 1);
+  for (uint32_t i = 0; i < used; ++i) bw.put(sym_bits, first4[i]);
+  if (used == 4) bw.put(1, depth[first4[0]] == 1 ? 1u : 0u);
 }
 
 }  // namespace bro

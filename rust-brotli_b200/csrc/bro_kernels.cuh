@@ -1894,79 +1894,45 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split_greedy(Workspace W) {
 #define HDR_SECTIONS 5
 #define SECT_BYTES 65536  // worst case: 16384 context-map symbols of <= 21 bits + their prefix code
 
-// Warp-cooperative huff_create_tree(): the (count asc, symbol desc) order is a total order, so any correct sort gives
-// the reference's node order -- here a bitonic sort of 64-bit keys in shared memory by all 32 lanes; the two-queue
-// merge and the depth assignment stay serial on lane 0.  Must be called by the whole warp.
-__device__ __forceinline__ void huff_create_tree_warp(const uint32_t* data, uint32_t length, int tree_limit, HuffNode* tree,
-                                                      uint8_t* depth, uint64_t* keys /* smem, 1024 */) {
+// Warp-cooperative front end of huff_code_lengths(): the used symbols are compacted into ws->key with ballots and sorted by a
+// bitonic network over shared memory (keys are unique, so any correct sort gives the order of the sequential specification);
+// the two-queue merge and the depth sweep then run on lane 0.  Must be called by the whole warp.  Returns the number of used symbols.
+__device__ __forceinline__ uint32_t huff_sorted_keys_warp(const uint32_t* counts, uint32_t length, uint64_t* keys /* smem, 1024 */) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t FULL = 0xffffffffu;
-  for (uint32_t count_limit = 1;; count_limit *= 2) {
-    // compaction of the used symbols (order irrelevant)
-    uint32_t n = 0;
-    for (uint32_t base = 0; base < length; base += 32) {
-      const uint32_t i = base + lane;
-      const uint32_t c = i < length ? data[i] : 0u;
-      const uint32_t bal = __ballot_sync(FULL, c != 0);
-      if (c) keys[n + __popc(bal & ((1u << lane) - 1u))] = ((uint64_t)bmax(c, count_limit) << 16) | (0xFFFFu - i);
-      n += __popc(bal);
-    }
-    if (n == 1) {
-      if (lane == 0) depth[0xFFFFu - (uint32_t)(keys[0] & 0xFFFFu)] = 1;
-      __syncwarp();
-      return;
-    }
-    uint32_t np = 1;
-    while (np < n) np <<= 1;
-    for (uint32_t i = n + lane; i < np; i += 32) keys[i] = ~0ull;
-    __syncwarp();
-    for (uint32_t k = 2; k <= np; k <<= 1) {
-      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-        for (uint32_t t = lane; t < (np >> 1); t += 32) {
-          const uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j clear
-          const uint32_t hi = lo | j;
-          const bool up = (lo & k) == 0;
-          const uint64_t a = keys[lo], b = keys[hi];
-          if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
-        }
-        __syncwarp();
-      }
-    }
-    for (uint32_t i = lane; i < n; i += 32) {
-      const uint64_t kv = keys[i];
-      tree[i].count = (uint32_t)(kv >> 16);
-      tree[i].left = -1;
-      tree[i].right_or_value = (int16_t)(0xFFFFu - (uint32_t)(kv & 0xFFFFu));
-    }
-    __syncwarp();
-    int ok = 0;
-    if (lane == 0) {
-      HuffNode sentinel;
-      sentinel.count = 0xFFFFFFFFu; sentinel.left = -1; sentinel.right_or_value = -1;
-      tree[n] = sentinel;
-      tree[n + 1] = sentinel;
-      uint32_t i = 0, j = n + 1;
-      for (uint32_t k = n - 1; k != 0; --k) {
-        uint32_t left, right;
-        if (tree[i].count <= tree[j].count) left = i++; else left = j++;
-        if (tree[i].count <= tree[j].count) right = i++; else right = j++;
-        const uint32_t j_end = 2 * n - k;
-        tree[j_end].count = tree[left].count + tree[right].count;
-        tree[j_end].left = (int16_t)left;
-        tree[j_end].right_or_value = (int16_t)right;
-        tree[j_end + 1] = sentinel;
-      }
-      ok = huff_set_depth((int)(2 * n - 1), tree, depth, tree_limit) ? 1 : 0;
-    }
-    ok = __shfl_sync(FULL, ok, 0);
-    if (ok) return;
+  uint32_t n = 0;
+  for (uint32_t base = 0; base < length; base += 32) {
+    const uint32_t i = base + lane;
+    const uint32_t c = i < length ? counts[i] : 0u;
+    const uint32_t bal = __ballot_sync(FULL, c != 0);
+    if (c) keys[n + __popc(bal & ((1u << lane) - 1u))] = ((uint64_t)c << 16) | i;
+    n += __popc(bal);
   }
+  if (n < 2) { __syncwarp(); return n; }
+  uint32_t np = 1;
+  while (np < n) np <<= 1;
+  for (uint32_t i = n + lane; i < np; i += 32) keys[i] = ~0ull;
+  __syncwarp();
+  for (uint32_t k = 2; k <= np; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t t = lane; t < (np >> 1); t += 32) {
+        const uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j clear
+        const uint32_t hi = lo | j;
+        const bool up = (lo & k) == 0;
+        const uint64_t a = keys[lo], b = keys[hi];
+        if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+      }
+      __syncwarp();
+    }
+  }
+  return n;
 }
 
 __global__ void __launch_bounds__(32) k_trees(Workspace W) {
-  __shared__ HuffStoreWs ws_s;  // tree / serialisation scratch in shared memory: the serial parts are latency bound
-  __shared__ uint64_t s_keys[1024];
+  __shared__ HuffWs ws_s;  // code construction / serialisation scratch in shared memory: the serial parts are latency bound
   __shared__ uint8_t s_depth[704];
+  __shared__ uint16_t s_code[704];
+  __shared__ uint32_t s_hist[704];
   const uint32_t m = blockIdx.y;
   const uint32_t lane = threadIdx.x;
   const MBDesc& mb = W.mb[m];
@@ -2013,61 +1979,45 @@ __global__ void __launch_bounds__(32) k_trees(Workspace W) {
     depth = W.dist_depth + ((size_t)m * W.max_dist_types + t) * 64; code = W.dist_code + ((size_t)m * W.max_dist_types + t) * 64;
   }
   const uint32_t tree_cap = W.max_lit_trees + W.max_cmd_types + W.max_dist_types;
-  HuffStoreWs* ws = &ws_s;
-  // the histogram is worked on in shared memory: the RLE smoothing and the symbol scans below are serial, and on global
-  // memory every dependent access is an L2 round trip
-  __shared__ uint32_t s_hist[704];
-  uint32_t* const ghist = hist;
-  for (uint32_t i = lane; i < A; i += 32) s_hist[i] = ghist[i];
+  // == huff_build_and_store() with the sort done by the whole warp; everything is worked on in shared memory: the merge, the
+  // smoothing scan and the run-length coding are chains of dependent accesses ==
+  for (uint32_t i = lane; i < A; i += 32) { s_hist[i] = hist[i]; s_depth[i] = 0; s_code[i] = 0; }
   __syncwarp();
-  hist = s_hist;
-  if (P.use_rle_opt && lane == 0) huff_optimize_counts_for_rle(A, hist, ws->rle);
+  if (P.use_rle_opt && lane == 0) huff_smooth_counts(A, s_hist);
   __syncwarp();
-  for (uint32_t i = lane; i < A; i += 32) ghist[i] = s_hist[i];
-  // == huff_build_and_store(), with the tree construction done by the whole warp ==
-  __shared__ uint32_t s4[4];  // first four used symbols (kept in shared memory: see profiles/ notes on the local-array clobber)
-  uint32_t count = 0, max_bits = 0;
-  if (lane < 4) s4[lane] = 0;
-  __syncwarp();
-  for (uint32_t i = 0; i < A; ++i) {  // (uniform across lanes; reads are broadcast)
-    if (hist[i]) {
-      if (count < 4) { if (lane == 0) s4[count] = i; }
-      else if (count > 4) break;
-      count++;
-    }
-  }
-  __syncwarp();
+  uint32_t max_bits = 0;
   for (uint32_t c = A - 1; c; c >>= 1) ++max_bits;
-  for (uint32_t i = lane; i < A; i += 32) { s_depth[i] = 0; depth[i] = 0; code[i] = 0; }
-  __syncwarp();
+  const uint32_t used = huff_sorted_keys_warp(s_hist, A, ws_s.key);
   BitWriter bw;
   bw.init(W.tree_bits + ((size_t)m * tree_cap + slot) * TREE_SLOT_BYTES);
-  if (count <= 1) {
-    if (lane == 0) { bw.put(4, 1); bw.put(max_bits, s4[0]); }
-  } else {
-    huff_create_tree_warp(hist, A, 15, ws->nodes, s_depth, s_keys);
-    __syncwarp();
-    if (lane == 0) {
-      huff_depths_to_codes(s_depth, A, code);
-      if (count <= 4) {
+  if (lane == 0) {
+    if (used <= 1) {
+      bw.put(4, 1);
+      bw.put(max_bits, used ? (uint32_t)(ws_s.key[0] & 0xFFFFu) : 0u);
+    } else {
+      huff_lengths_sorted(&ws_s, used, 15, s_depth);
+      huff_depths_to_codes(s_depth, A, s_code);
+      if (used > 4) huff_store_complex(bw, s_depth, A, &ws_s);
+      else {  // simple code: symbols by code length, then by value (ws_s.key is sorted by count, so re-derive from the alphabet)
+        uint32_t first4[4] = {0, 0, 0, 0}, k = 0;
+        for (uint32_t i = 0; i < A && k < used; ++i) if (s_hist[i]) first4[k++] = i;
+        for (uint32_t i = 1; i < used; ++i) {
+          const uint32_t v = first4[i];
+          uint32_t j = i;
+          for (; j > 0 && s_depth[first4[j - 1]] > s_depth[v]; --j) first4[j] = first4[j - 1];
+          first4[j] = v;
+        }
         bw.put(2, 1);
-        bw.put(2, count - 1);
-        for (uint32_t i = 0; i < count; ++i)
-          for (uint32_t j = i + 1; j < count; ++j)
-            if (s_depth[s4[j]] < s_depth[s4[i]]) { uint32_t tt = s4[j]; s4[j] = s4[i]; s4[i] = tt; }
-        for (uint32_t i = 0; i < count; ++i) bw.put(max_bits, s4[i]);
-        if (count == 4) bw.put(1, s_depth[s4[0]] == 1 ? 1u : 0u);
-      } else {
-        huff_store_complex(bw, s_depth, A, ws);
+        bw.put(2, used - 1);
+        for (uint32_t i = 0; i < used; ++i) bw.put(max_bits, first4[i]);
+        if (used == 4) bw.put(1, s_depth[first4[0]] == 1 ? 1u : 0u);
       }
     }
-    __syncwarp();
-    for (uint32_t i = lane; i < A; i += 32) depth[i] = s_depth[i];
-  }
-  if (lane == 0) {
     bw.flush_partial();
     W.tree_nbits[(size_t)m * tree_cap + slot] = (uint32_t)bw.bit_pos();
   }
+  __syncwarp();
+  for (uint32_t i = lane; i < A; i += 32) { depth[i] = s_depth[i]; code[i] = s_code[i]; }
 }
 
 __device__ __forceinline__ void append_bits(BitWriter& bw, const uint8_t* src, uint32_t nbits) {
@@ -2083,31 +2033,65 @@ __device__ __forceinline__ void append_bits(BitWriter& bw, const uint8_t* src, u
   }
 }
 
+// k_header: lane 0 writes the metablock prologue and the block-split / context-map sections, then the whole warp splices the
+// per-code descriptions behind them at bit granularity (32-bit chunks, atomicOr into the zeroed tail of the header buffer).
 __global__ void __launch_bounds__(32) k_header(Workspace W) {
   const uint32_t m = blockIdx.x;
-  if (threadIdx.x != 0) return;
+  const uint32_t lane = threadIdx.x;
   MBDesc& mb = W.mb[m];
   const uint32_t nctx = ctxmap_num_contexts(mb.ctx_map_id);
-  HuffStoreWs* ws = W.huff_ws + m;
   SplitView lv = make_view(W, m, 0), cv = make_view(W, m, 1), dv = make_view(W, m, 2);
-  BitWriter bw;
-  bw.init(W.hdr + (size_t)m * W.hdr_cap);
-  store_compressed_metablock_header(bw, false, mb.len);
-  const uint8_t* sect = W.sect_bits + (size_t)m * HDR_SECTIONS * SECT_BYTES;
-  const uint32_t* snb = W.sect_nbits + (size_t)m * HDR_SECTIONS;
-  for (uint32_t k = 0; k < 3; ++k) append_bits(bw, sect + (size_t)k * SECT_BYTES, snb[k]);  // block-split codes
-  bw.put(2, 0);
-  bw.put(4, 0);
-  for (uint32_t i = 0; i < lv.num_types; ++i) bw.put(2, mb.ctx_map_id == CTXMAP_FULL_SIGNED ? 3 : 2);  // CONTEXT_SIGNED / CONTEXT_UTF8
-  append_bits(bw, sect + (size_t)3 * SECT_BYTES, snb[3]);  // literal context map
-  append_bits(bw, sect + (size_t)4 * SECT_BYTES, snb[4]);  // distance context map
+  uint8_t* hdr = W.hdr + (size_t)m * W.hdr_cap;
+  uint64_t pos = 0;
+  if (lane == 0) {
+    BitWriter bw;
+    bw.init(hdr);
+    store_compressed_metablock_header(bw, false, mb.len);
+    const uint8_t* sect = W.sect_bits + (size_t)m * HDR_SECTIONS * SECT_BYTES;
+    const uint32_t* snb = W.sect_nbits + (size_t)m * HDR_SECTIONS;
+    for (uint32_t k = 0; k < 3; ++k) append_bits(bw, sect + (size_t)k * SECT_BYTES, snb[k]);  // block-split codes
+    bw.put(2, 0);
+    bw.put(4, 0);
+    for (uint32_t i = 0; i < lv.num_types; ++i) bw.put(2, mb.ctx_map_id == CTXMAP_FULL_SIGNED ? 3 : 2);  // CONTEXT_SIGNED / CONTEXT_UTF8
+    append_bits(bw, sect + (size_t)3 * SECT_BYTES, snb[3]);  // literal context map
+    append_bits(bw, sect + (size_t)4 * SECT_BYTES, snb[4]);  // distance context map
+    bw.flush_partial();
+    pos = bw.bit_pos();
+  }
+  pos = __shfl_sync(0xffffffffu, pos, 0);
   const uint32_t tree_cap = W.max_lit_trees + W.max_cmd_types + W.max_dist_types;
   const bool full = mb.ctx_map_id >= CTXMAP_FULL_UTF8;
   const uint32_t ntrees = (full ? W.cm_counts[(size_t)m * 2] : lv.num_types * nctx) + cv.num_types + (full ? W.cm_counts[(size_t)m * 2 + 1] : dv.num_types);
-  for (uint32_t t = 0; t < ntrees; ++t)
-    append_bits(bw, W.tree_bits + ((size_t)m * tree_cap + t) * TREE_SLOT_BYTES, W.tree_nbits[(size_t)m * tree_cap + t]);
-  bw.flush_partial();
-  mb.hdr_bits = (uint32_t)bw.bit_pos();
+  const uint32_t* tnb = W.tree_nbits + (size_t)m * tree_cap;
+  uint64_t total = 0;
+  for (uint32_t t = lane; t < ntrees; t += 32) total += tnb[t];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+  // zero everything behind the prologue's last (partial) byte up to the end of the spliced region, word by word
+  {
+    const uint64_t first_byte = (pos + 7) >> 3, last_byte = ((pos + total + 7) >> 3) + 8;
+    for (uint64_t i = first_byte + lane; i < ((first_byte + 3) & ~3ull); i += 32) hdr[i] = 0;
+    uint32_t* hw = reinterpret_cast<uint32_t*>(hdr);
+    for (uint64_t w = ((first_byte + 3) >> 2) + lane; w < (last_byte + 3) >> 2; w += 32) hw[w] = 0;
+  }
+  __syncwarp();
+  uint32_t* hw = reinterpret_cast<uint32_t*>(hdr);
+  for (uint32_t t = 0; t < ntrees; ++t) {
+    const uint32_t nb = tnb[t];
+    const uint8_t* src = W.tree_bits + ((size_t)m * tree_cap + t) * TREE_SLOT_BYTES;
+    for (uint32_t c = lane; c * 32 < nb; c += 32) {
+      const uint32_t left = nb - c * 32;
+      uint32_t v = (uint32_t)src[c * 4] | ((uint32_t)src[c * 4 + 1] << 8) | ((uint32_t)src[c * 4 + 2] << 16) | ((uint32_t)src[c * 4 + 3] << 24);
+      if (left < 32) v &= (1u << left) - 1u;
+      const uint64_t bp = pos + (uint64_t)c * 32;
+      const uint32_t sh = (uint32_t)(bp & 31);
+      atomicOr(&hw[bp >> 5], v << sh);
+      if (sh) atomicOr(&hw[(bp >> 5) + 1], v >> (32 - sh));
+    }
+    pos += nb;
+  }
+  __syncwarp();
+  if (lane == 0) mb.hdr_bits = (uint32_t)pos;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -11,7 +11,10 @@ from tools.model_harness import Model
 SRC = "/root/reference/testdata"
 FILES = ["alice29.txt", "asyoulik.txt", "random_then_unicode", "quickfox_repeated", "random_org_10k.bin", "backward65536",
          "64x", "ukkonooa", "monkey", "x", "xyzzy", "10x10y", "aaabaaaa", "empty", "quickfox", "compressed_file"]
-CONFIGS = [(5, 20), (5, 22), (6, 22), (7, 22), (8, 22), (9, 22), (9, 16), (5, 24), (5, 18)]
+CONFIGS = [(5, 20), (5, 22), (6, 22), (7, 22), (8, 22), (9, 22), (9, 16), (5, 24), (5, 18), (10, 22), (11, 22), (11, 24), (10, 16)]
+# quality >= 10: oracle/brotli_ref.c restates the q4..q9 path only; the size reference there is libbrotlienc 1.1.0 (the C code
+# the reference was ported from: alice29 q10 = 47 477 B, q11 = 46 487 B against the reference's own KATs 47 488 / 46 493,
+# src/bin/integration_tests.rs:408-449) -- "oracle_size" then holds that size and "size_reference" says so.
 
 def main():
     here = os.path.dirname(os.path.abspath(__file__))
@@ -21,9 +24,16 @@ def main():
         shutil.copyfile(os.path.join(SRC, f), os.path.join(here, f))
         d = open(os.path.join(here, f), "rb").read()
         for q, w in CONFIGS:
+            sc = sys_compress(d, q, w)
+            if q >= 10:
+                mc, _ = m.compress(d, q, w)
+                assert sys_decompress(mc, len(d)) == d
+                table["%s|q%d|w%d" % (f, q, w)] = {
+                    "input_size": len(d), "oracle_size": len(sc), "size_reference": "libbrotlienc", "libbrotlienc_size": len(sc),
+                    "model_size": len(mc), "model_sha256": hashlib.sha256(mc).hexdigest()}
+                continue
             oc, st = o.compress(d, q, w)
             assert sys_decompress(oc, len(d)) == d
-            sc = sys_compress(d, q, w)
             mc, _ = m.compress(d, q, w)
             assert sys_decompress(mc, len(d)) == d
             table["%s|q%d|w%d" % (f, q, w)] = {

@@ -14,7 +14,7 @@ FILES = ["alice29.txt", "asyoulik.txt", "random_then_unicode", "quickfox_repeate
 
 
 @pytest.mark.parametrize("name", FILES)
-@pytest.mark.parametrize("q,w", [(5, 20), (5, 22), (7, 22), (9, 22), (9, 16), (5, 18)])
+@pytest.mark.parametrize("q,w", [(5, 20), (5, 22), (7, 22), (9, 22), (9, 16), (5, 18), (10, 22), (11, 22), (11, 24), (10, 16)])
 def test_model_golden_roundtrip_and_size(model, golden_table, name, q, w):
     d = golden_bytes(name)
     c, _ = model.compress(d, q, w)
@@ -22,6 +22,28 @@ def test_model_golden_roundtrip_and_size(model, golden_table, name, q, w):
     g = golden_table["%s|q%d|w%d" % (name, q, w)]
     assert hashlib.sha256(c).hexdigest() == g["model_sha256"]
     assert_size_parity(len(c), g["oracle_size"], "%s q%d w%d" % (name, q, w))
+
+
+def test_model_against_reference_kats_q10_q11(model):
+    """The reference's own exact size vectors for the binary-tree / Zopfli qualities (src/bin/integration_tests.rs:408-449):
+    alice29.txt, lgwin 22: quality 10 -> 47 488 B, quality 11 -> 46 493 B.  The pipeline must land within +-0.5 %."""
+    d = golden_bytes("alice29.txt")
+    for q, pin in ((10, 47488), (11, 46493)):
+        c, _ = model.compress(d, q, 22)
+        assert sys_decompress(c, len(d)) == d
+        assert abs(len(c) - pin) <= pin * 0.005, (q, len(c), pin)
+
+
+def test_model_hq_options(model):
+    """quality 10 / 11 knobs: every variant is a valid stream; the histogram stage (BrotliSplitBlock + context maps) and the
+    static dictionary each pay for themselves on English text."""
+    d = golden_bytes("asyoulik.txt")
+    base = len(model.compress(d, 10, 22)[0])
+    for kw in ({"hq_split": 0}, {"use_dict": 0}, {"ctx_model": 0}, {"unit": 65536, "mb_units": 64}, {"depth": 256}):
+        c, _ = model.compress(d, 10, 22, **kw)
+        assert sys_decompress(c, len(d)) == d
+        if "unit" not in kw and "depth" not in kw:
+            assert len(c) > base, kw
 
 
 @pytest.mark.parametrize("shards", [1, 2, 3, 5])
