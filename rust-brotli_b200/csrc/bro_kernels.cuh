@@ -145,6 +145,49 @@ __device__ __forceinline__ MetaCodes make_codes(const Workspace& W, uint32_t m) 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// TMA bulk copies (sm_90+ `cp.async.bulk`, SASS UBLKCP): a contiguous tile travels global -> shared memory through the copy
+// engine and signals an mbarrier with its byte count; no thread spends issue slots on LDG / STS pairs or address arithmetic.
+// Addresses and sizes must be multiples of 16 bytes.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(arrivals) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_addr_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MBAR_DONE;\n"
+      "bra MBAR_WAIT;\n"
+      "MBAR_DONE:\n"
+      "}" ::"r"(smem_addr_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// The whole CTA calls this: thread 0 arms the barrier and issues one bulk copy of `bytes` (multiple of 16, both addresses 16-byte
+// aligned), everybody waits for the bytes to land.
+__device__ __forceinline__ void tma_stage_tile(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, bytes);
+    tma_load_1d(smem_dst, gmem_src, bytes, bar);
+  }
+  mbar_wait(bar, 0);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Radix sort of the positions of one batch by bucket key (stable => ascending position inside a bucket).
 // Pass 0 sorts by key & 0xFF reading the input bytes; pass 1 by key >> 8 reading the packed words of pass 0.
 // Element word: (key >> 8) << 25 | (position - batch_origin).
@@ -174,18 +217,19 @@ __device__ __forceinline__ uint32_t smem_key(const uint32_t* sw, uint32_t e, int
   return hash_key_from_words(hash_type, key_bits, lo, hi);
 }
 
-__device__ __forceinline__ void sort_stage_tile(const SortArgs& a, uint32_t tile, uint32_t* sw) {
-  // stage SORT_TILE + 8 bytes (input is padded, so reading past `count` is safe)
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(a.data) + (size_t)tile * (SORT_TILE / 4);
-  for (uint32_t i = threadIdx.x; i < SORT_TILE / 4 + 4; i += SORT_THREADS) sw[i] = src[i];
+__device__ __forceinline__ void sort_stage_tile(const SortArgs& a, uint32_t tile, uint32_t* sw, uint64_t* bar) {
+  // stage SORT_TILE + 16 bytes with one TMA bulk copy (the input is padded, so reading past `count` is safe; the batch origin
+  // is 4096-byte aligned)
+  tma_stage_tile(sw, a.data + (size_t)tile * SORT_TILE, SORT_TILE + 16, bar);
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(SortArgs a) {
-  __shared__ uint32_t sw[SORT_TILE / 4 + 4];
+  __shared__ __align__(16) uint32_t sw[SORT_TILE / 4 + 4];
+  __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t sh[256];
   const uint32_t tile = blockIdx.x;
   sh[threadIdx.x] = 0;
-  if (a.pass == 0) sort_stage_tile(a, tile, sw);
+  if (a.pass == 0) sort_stage_tile(a, tile, sw, &s_bar);
   __syncthreads();
   const uint32_t base = tile * SORT_TILE;
 #pragma unroll 4
@@ -244,13 +288,14 @@ __global__ void __launch_bounds__(256) k_scan_digits(const uint32_t* totals, uin
 }
 
 __global__ void __launch_bounds__(SORT_THREADS, 6) k_sort_scatter(SortArgs a) {
-  __shared__ uint32_t sw[SORT_TILE / 4 + 4];
+  __shared__ __align__(16) uint32_t sw[SORT_TILE / 4 + 4];
+  __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t wc[SORT_THREADS / 32][256];
   __shared__ uint32_t s_word[SORT_TILE];  // element words parked in shared memory (keeps the register count low => occupancy)
   const uint32_t tile = blockIdx.x;
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (uint32_t i = threadIdx.x; i < (SORT_THREADS / 32) * 256; i += SORT_THREADS) (&wc[0][0])[i] = 0;
-  if (a.pass == 0) sort_stage_tile(a, tile, sw);
+  if (a.pass == 0) sort_stage_tile(a, tile, sw, &s_bar);
   __syncthreads();
   const uint32_t base = tile * SORT_TILE;
   uint16_t lrank[SORT_ITEMS];
@@ -394,13 +439,27 @@ __device__ __forceinline__ void load16_unaligned(const uint8_t* p, uint32_t* w) 
   w[3] = __funnelshift_r(a3, a4, sh);
 }
 
+// Sorted positions of a CTA's entries [j0, j0 + E) -> s_pos: interior CTAs take them with one TMA bulk copy (j0 * 4 and E * 4 are
+// multiples of 16), the first / last CTA of a batch with guarded loads (0xFFFFFFFF = no entry).  Ends with a CTA barrier.
+__device__ __forceinline__ void match_stage_positions(const MatchArgs& a, int64_t j0, uint32_t E, uint32_t* s_pos, uint64_t* bar) {
+  if (j0 >= 0 && j0 + (int64_t)E <= (int64_t)a.count) {
+    tma_stage_tile(s_pos, a.sorted + j0, E * 4u, bar);
+  } else {
+    for (uint32_t i = threadIdx.x; i < E; i += MATCH_THREADS) {
+      const int64_t j = j0 + i;
+      s_pos[i] = (j >= 0 && j < (int64_t)a.count) ? a.sorted[j] : 0xFFFFFFFFu;
+    }
+  }
+  __syncthreads();
+}
+
 // dynamic shared memory: (MATCH_THREADS + depth) entries x 6 words.
 // Loop version: one position per lane walks its surviving candidates, nearest first (the direct form of the reference's
 // bucket walk).  Kept as the A/B baseline of k_match_shallow (B200_OPT_SHALLOW_MATCH = 0); deep buckets use k_match_deep.
 // DEPTH = bucket depth (compile time: every shared-memory array offset becomes an immediate).
 template <int DEPTH>
 __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
-  extern __shared__ uint32_t smem[];
+  extern __shared__ __align__(16) uint32_t smem[];
   constexpr uint32_t E = MATCH_THREADS + (uint32_t)DEPTH;
   uint32_t* s_pos = smem;
   uint32_t* s_key = smem + E;
@@ -409,15 +468,16 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
   uint32_t* s_d2 = smem + 4 * E;
   uint32_t* s_d3 = smem + 5 * E;
   const int64_t j0 = (int64_t)blockIdx.x * MATCH_THREADS - DEPTH;  // sorted index of smem entry 0
+  __shared__ __align__(8) uint64_t s_bar;
+  match_stage_positions(a, j0, E, s_pos, &s_bar);
   for (uint32_t i = threadIdx.x; i < E; i += MATCH_THREADS) {
-    int64_t j = j0 + i;
-    uint32_t pos = 0xFFFFFFFFu, key = 0xFFFFFFFFu, w[4] = {0, 0, 0, 0};
-    if (j >= 0 && j < (int64_t)a.count) {
-      pos = a.sorted[j];
+    const uint32_t pos = s_pos[i];
+    uint32_t key = 0xFFFFFFFFu, w[4] = {0, 0, 0, 0};
+    if (pos != 0xFFFFFFFFu) {
       load16_unaligned(a.data + a.origin + pos, w);
       key = hash_key_from_words(a.hash_type, a.key_bits, w[0], w[1]);
     }
-    s_pos[i] = pos; s_key[i] = key; s_d0[i] = w[0]; s_d1[i] = w[1]; s_d2[i] = w[2]; s_d3[i] = w[3];
+    s_key[i] = key; s_d0[i] = w[0]; s_d1[i] = w[1]; s_d2[i] = w[2]; s_d3[i] = w[3];
   }
   __syncthreads();
   const uint32_t i = threadIdx.x + (uint32_t)DEPTH;
@@ -489,7 +549,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
 // (divergent) evaluation.  Result identical to the sequential newest-first walk: highest score, nearest on ties.
 template <int DEPTH>
 __global__ void __launch_bounds__(MATCH_THREADS) k_match_shallow(MatchArgs a) {
-  extern __shared__ uint32_t smem[];
+  extern __shared__ __align__(16) uint32_t smem[];
   constexpr uint32_t E = MATCH_THREADS + (uint32_t)DEPTH;
   uint32_t* s_pos = smem;
   uint32_t* s_key = smem + E;
@@ -498,15 +558,16 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_shallow(MatchArgs a) {
   uint32_t* s_d2 = smem + 4 * E;
   uint32_t* s_d3 = smem + 5 * E;
   const int64_t j0 = (int64_t)blockIdx.x * MATCH_THREADS - DEPTH;
+  __shared__ __align__(8) uint64_t s_bar;
+  match_stage_positions(a, j0, E, s_pos, &s_bar);
   for (uint32_t i = threadIdx.x; i < E; i += MATCH_THREADS) {
-    int64_t j = j0 + i;
-    uint32_t pos = 0xFFFFFFFFu, key = 0xFFFFFFFFu, w[4] = {0, 0, 0, 0};
-    if (j >= 0 && j < (int64_t)a.count) {
-      pos = a.sorted[j];
+    const uint32_t pos = s_pos[i];
+    uint32_t key = 0xFFFFFFFFu, w[4] = {0, 0, 0, 0};
+    if (pos != 0xFFFFFFFFu) {
       load16_unaligned(a.data + a.origin + pos, w);
       key = hash_key_from_words(a.hash_type, a.key_bits, w[0], w[1]);
     }
-    s_pos[i] = pos; s_key[i] = key; s_d0[i] = w[0]; s_d1[i] = w[1]; s_d2[i] = w[2]; s_d3[i] = w[3];
+    s_key[i] = key; s_d0[i] = w[0]; s_d1[i] = w[1]; s_d2[i] = w[2]; s_d3[i] = w[3];
   }
   __syncthreads();
   const uint32_t i = threadIdx.x + (uint32_t)DEPTH;
@@ -571,7 +632,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_shallow(MatchArgs a) {
   uint32_t outv = best_len ? ((best_dist << 8) | best_len) : 0u;
   if (best_len == 0 && a.use_dict && a.n - p >= 8)  // nothing in the bucket: static dictionary (mod.rs:1797, :1942)
     outv = dict_candidate_dev(a.dict, a.hash_type, s_d0[i], s_d1[i], s_d2[i], s_d3[i], a.data + p, a.n - p, bmin(p, a.max_backward));
-  a.best[p] = outv;
+  __stcs(&a.best[p], outv);  // scattered, written once, read much later by the parse: do not let it displace the input in L2
 }
 
 // Deep buckets (depth 64..256: q7..q9 and lgwin <= 16).  With one position per lane the survivors of the 4-byte filter are
@@ -582,7 +643,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_shallow(MatchArgs a) {
 // *previous* groups only (all nearer), which keeps it exact.
 template <int DEPTH>
 __global__ void __launch_bounds__(MATCH_THREADS) k_match_deep(MatchArgs a) {
-  extern __shared__ uint32_t smem[];
+  extern __shared__ __align__(16) uint32_t smem[];
   constexpr uint32_t E = MATCH_THREADS + (uint32_t)DEPTH;
   uint32_t* s_pos = smem;
   uint32_t* s_key = smem + E;
@@ -595,15 +656,16 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_deep(MatchArgs a) {
   __shared__ uint32_t s_snap[MATCH_THREADS / 32][32];  // best length of the previous groups
   __shared__ uint32_t s_far[MATCH_THREADS / 32];
   const int64_t j0 = (int64_t)blockIdx.x * MATCH_THREADS - DEPTH;
+  __shared__ __align__(8) uint64_t s_bar;
+  match_stage_positions(a, j0, E, s_pos, &s_bar);
   for (uint32_t i = threadIdx.x; i < E; i += MATCH_THREADS) {
-    int64_t j = j0 + i;
-    uint32_t pos = 0xFFFFFFFFu, key = 0xFFFFFFFFu, w[4] = {0, 0, 0, 0};
-    if (j >= 0 && j < (int64_t)a.count) {
-      pos = a.sorted[j];
+    const uint32_t pos = s_pos[i];
+    uint32_t key = 0xFFFFFFFFu, w[4] = {0, 0, 0, 0};
+    if (pos != 0xFFFFFFFFu) {
       load16_unaligned(a.data + a.origin + pos, w);
       key = hash_key_from_words(a.hash_type, a.key_bits, w[0], w[1]);
     }
-    s_pos[i] = pos; s_key[i] = key; s_d0[i] = w[0]; s_d1[i] = w[1]; s_d2[i] = w[2]; s_d3[i] = w[3];
+    s_key[i] = key; s_d0[i] = w[0]; s_d1[i] = w[1]; s_d2[i] = w[2]; s_d3[i] = w[3];
   }
   __syncthreads();
   const uint32_t FULL = 0xffffffffu;

@@ -28,23 +28,24 @@ struct MatchAllArgs {
 
 template <int DEPTH>
 __global__ void __launch_bounds__(MATCH_THREADS) k_match_all(MatchAllArgs A) {
-  extern __shared__ uint32_t smem[];
+  extern __shared__ __align__(16) uint32_t smem[];
+  __shared__ __align__(8) uint64_t s_bar;
   const MatchArgs& a = A.m;
   constexpr uint32_t E = MATCH_THREADS + (uint32_t)DEPTH;
   uint32_t* s_pos = smem;
   uint32_t* s_key = smem + E;
   uint32_t* s_d0 = smem + 2 * E;
   const int64_t j0 = (int64_t)blockIdx.x * MATCH_THREADS - DEPTH;
+  match_stage_positions(a, j0, E, s_pos, &s_bar);  // TMA bulk copy of the CTA's slice of the sorted list
   for (uint32_t i = threadIdx.x; i < E; i += MATCH_THREADS) {
-    const int64_t j = j0 + i;
-    uint32_t pos = 0xFFFFFFFFu, key = 0xFFFFFFFFu, w0 = 0;
-    if (j >= 0 && j < (int64_t)a.count) {
-      pos = a.sorted[j];
+    const uint32_t pos = s_pos[i];
+    uint32_t key = 0xFFFFFFFFu, w0 = 0;
+    if (pos != 0xFFFFFFFFu) {
       const uint8_t* p = a.data + a.origin + pos;
       w0 = ldu32(p);
       key = hash_key_from_words(a.hash_type, a.key_bits, w0, (uint32_t)p[4]);
     }
-    s_pos[i] = pos; s_key[i] = key; s_d0[i] = w0;
+    s_key[i] = key; s_d0[i] = w0;
   }
   __syncthreads();
   const uint32_t i = threadIdx.x + (uint32_t)DEPTH;
