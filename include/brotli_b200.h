@@ -138,7 +138,8 @@ B200Encoder* b200_encoder_create(int device);
 void b200_encoder_destroy(B200Encoder* e);
 int b200_encoder_set_option(B200Encoder* e, int option, uint32_t value);
 size_t b200_max_compressed_size(size_t n);
-/* device_io != 0: in/out are device pointers on the encoder's GPU */
+/* device_io: 0 = in / out are host pointers; 1 = both are device pointers on the encoder's GPU; 2 = host input, device output
+ * (e.g. shard outputs that travel on to a peer GPU over NVLink); 3 = device input, host output */
 int b200_encoder_compress(B200Encoder* e, int quality, int lgwin, const uint8_t* in, size_t n, uint8_t* out, size_t out_cap,
                           size_t* out_size, int device_io);
 int b200_encoder_compress_range(B200Encoder* e, int quality, int lgwin, uint64_t size_hint, const uint8_t* in, size_t n,

@@ -29,11 +29,11 @@ namespace bro {
 struct BsParams {
   uint32_t A, per_hist, max_hist, stride, switch_cost_q16;
 };
-BRO_HD BsParams bs_params(int cat) {  // block_splitter.rs:21-45
+BRO_HD BsParams bs_params(int cat, uint32_t dist_A = 64) {  // block_splitter.rs:21-45
   BsParams p;
   if (cat == 0) { p.A = 256; p.per_hist = 544; p.max_hist = 100; p.stride = 70; p.switch_cost_q16 = 1841562u; }       // 28.1
   else if (cat == 1) { p.A = 704; p.per_hist = 530; p.max_hist = 50; p.stride = 40; p.switch_cost_q16 = 884736u; }    // 13.5
-  else { p.A = 64; p.per_hist = 544; p.max_hist = 50; p.stride = 40; p.switch_cost_q16 = 956826u; }                   // 14.6
+  else { p.A = dist_A; p.per_hist = 544; p.max_hist = 50; p.stride = 40; p.switch_cost_q16 = 956826u; }                   // 14.6
   return p;
 }
 
@@ -291,8 +291,9 @@ struct BsSplit {
 };
 
 // SplitByteVector (block_splitter.rs:692-837) + ClusterBlocks (:399-690).  syms[i] & mask is the symbol.
-inline void bs_split_vector(const uint16_t* syms, uint32_t mask, uint32_t count, int cat, uint32_t max_blocks, const uint32_t* lut, BsSplit* out) {
-  const BsParams p = bs_params(cat);
+inline void bs_split_vector(const uint16_t* syms, uint32_t mask, uint32_t count, int cat, uint32_t max_blocks, const uint32_t* lut, BsSplit* out,
+                            uint32_t dist_A = 64) {
+  const BsParams p = bs_params(cat, dist_A);
   const uint32_t A = p.A;
   out->types.clear();
   out->lengths.clear();

@@ -203,6 +203,55 @@ BRO_HD void prefix_encode_copy_distance(uint32_t distance_code, uint32_t* sym_nb
   }
 }
 
+// General form with NPOSTFIX / NDIRECT (PrefixEncodeCopyDistance, command.rs:134-173); quality >= 10 searches these per metablock.
+BRO_HD void prefix_encode_copy_distance_params(uint32_t distance_code, uint32_t npostfix, uint32_t ndirect, uint32_t* sym_nbits, uint32_t* extra) {
+  if (distance_code < 16u + ndirect) {
+    *sym_nbits = distance_code;
+    *extra = 0;
+    return;
+  }
+  const uint32_t dist = (1u << (npostfix + 2u)) + (distance_code - 16u - ndirect);
+  const uint32_t bucket = log2_floor_nz(dist) - 1u;
+  const uint32_t postfix = dist & ((1u << npostfix) - 1u);
+  const uint32_t prefix = (dist >> bucket) & 1u;
+  const uint32_t offset = (2u + prefix) << bucket;
+  const uint32_t nbits = bucket - npostfix;
+  *sym_nbits = (nbits << 10) | (16u + ndirect + ((2u * (nbits - 1u) + prefix) << npostfix) + postfix);
+  *extra = (dist - offset) >> npostfix;
+}
+// distance code of a command that was encoded with NPOSTFIX = NDIRECT = 0 (Command::restore_distance_code, command.rs:176-200)
+BRO_HD uint32_t restore_distance_code00(uint32_t sym_nbits, uint32_t extra) {
+  const uint32_t sym = sym_nbits & 0x3ffu;
+  if (sym < 16) return sym;
+  const uint32_t nbits = sym_nbits >> 10, hcode = sym - 16u;
+  return ((2u + (hcode & 1u)) << nbits) - 4u + extra + 16u;
+}
+BRO_HD uint32_t distance_alphabet_size(uint32_t npostfix, uint32_t ndirect) { return 16u + ndirect + (48u << npostfix); }
+#define BRO_DIST_A_MAX 544u  // histogram width of the distance alphabet when NPOSTFIX / NDIRECT are searched (<= 520 symbols)
+// The reference's search order over (NPOSTFIX, NDIRECT) given the cost of every combination (metablock.rs:152-207):
+// cost[npostfix * 16 + ndirect_msb], ndirect = ndirect_msb << npostfix.  Returns npostfix | ndirect << 8.
+BRO_HD uint32_t choose_distance_params(const uint64_t* cost) {
+  uint64_t best = ~0ull;
+  uint32_t best_np = 0, best_nd = 0, msb = 0;
+  bool check_orig = true;
+  for (uint32_t np = 0; np <= 3; ++np) {
+    while (msb < 16) {
+      const uint32_t nd = msb << np;
+      if (np == 0 && nd == 0) check_orig = false;
+      const uint64_t c = cost[np * 16 + msb];
+      if (c > best) break;
+      best = c;
+      best_np = np;
+      best_nd = nd;
+      ++msb;
+    }
+    if (msb > 0) --msb;
+    msb /= 2;
+  }
+  if (check_orig && cost[0] < best) { best_np = 0; best_nd = 0; }
+  return best_np | (best_nd << 8);
+}
+
 // Final command record produced by the command-finalise stage (the analogue of command.rs:11-21).
 struct Cmd {
   uint32_t insert_len;

@@ -85,15 +85,15 @@ struct EventPool {
 struct Lane {
   cudaStream_t stream = nullptr;
   DevBuf d_sortA, d_sortB, d_hist, d_digit, d_best, d_raw, d_unit, d_cmds, d_cmd_bits, d_lit_syms, d_cmd_syms, d_dist_syms,
-      d_hqm, d_hqn, d_hq_nodes, d_hq_pre, d_hq_scratch, d_bs_meta, d_bs_blockid, d_bs_signal, d_bs_hist, d_bs_icost, d_bs_first, d_bs_bstart,
-      d_bs_bh_in, d_bs_bh_work, d_bs_u64, d_bs_u32, d_bs_nsurv, d_cm_in, d_cm_work, d_cm_u64, d_cm_u32, d_cm_nsurv, d_cm_counts, d_cm_maps, d_mb, d_split_u8, d_split_u32, d_split_counts, d_hist_lit, d_hist_cmd, d_hist_dist, d_split_codes, d_codes_u8,
+      d_hqm, d_hqn, d_hq_nodes, d_hq_pre, d_hq_scratch, d_bs_meta, d_bs_blockid, d_bs_signal, d_bs_hist, d_bs_icost, d_bs_first, d_bs_fmap, d_bs_bstart,
+      d_bs_bh_in, d_bs_bh_work, d_bs_u64, d_bs_u32, d_bs_nsurv, d_cm_in, d_cm_work, d_cm_u64, d_cm_u32, d_cm_nsurv, d_cm_counts, d_cm_maps, d_dist_cost, d_mb, d_split_u8, d_split_u32, d_split_counts, d_hist_lit, d_hist_cmd, d_hist_dist, d_split_codes, d_codes_u8,
       d_codes_u16, d_hdr, d_huff_ws, d_ctxmap_ws, d_tree_ws, d_tree_bits, d_tree_nbits, d_cmd_tile, d_long_tab, d_seg_bits, d_sect_bits, d_sect_nbits;
   EventPool marks;  // timing marks: (event, stage that starts there); -1 ends the last stage
   std::vector<int> mark_stage;
   void release() {
     DevBuf* all[] = {&d_hqm, &d_hqn, &d_hq_nodes, &d_hq_pre, &d_hq_scratch, &d_bs_meta, &d_bs_blockid, &d_bs_signal, &d_bs_hist, &d_bs_icost,
-                     &d_bs_first, &d_bs_bstart, &d_bs_bh_in, &d_bs_bh_work, &d_bs_u64, &d_bs_u32, &d_bs_nsurv, &d_cm_in, &d_cm_work, &d_cm_u64,
-                     &d_cm_u32, &d_cm_nsurv, &d_cm_counts, &d_cm_maps, &d_sortA, &d_sortB, &d_hist, &d_digit, &d_best, &d_raw, &d_unit, &d_cmds, &d_cmd_bits, &d_lit_syms,
+                     &d_bs_first, &d_bs_fmap, &d_bs_bstart, &d_bs_bh_in, &d_bs_bh_work, &d_bs_u64, &d_bs_u32, &d_bs_nsurv, &d_cm_in, &d_cm_work, &d_cm_u64,
+                     &d_cm_u32, &d_cm_nsurv, &d_cm_counts, &d_cm_maps, &d_dist_cost, &d_sortA, &d_sortB, &d_hist, &d_digit, &d_best, &d_raw, &d_unit, &d_cmds, &d_cmd_bits, &d_lit_syms,
                      &d_cmd_syms, &d_dist_syms, &d_mb, &d_split_u8, &d_split_u32, &d_split_counts, &d_hist_lit, &d_hist_cmd,
                      &d_hist_dist, &d_split_codes, &d_codes_u8, &d_codes_u16, &d_hdr, &d_huff_ws, &d_ctxmap_ws, &d_tree_ws,
                      &d_tree_bits, &d_tree_nbits, &d_cmd_tile, &d_long_tab, &d_seg_bits, &d_sect_bits, &d_sect_nbits};
@@ -113,6 +113,7 @@ struct B200Encoder {
   uint32_t unit = 4096, mb_units = 1024, lcap = 64;
   int use_rle_opt = 1, split = 1, ctx_model = 1, use_dict = 1, hq_split = 1;
   uint32_t hq_unit = 16384;  // parse unit of the shortest-path parse (quality >= 10)
+  int hq_thread_units = 0;   // 1: one parse unit per thread instead of one per warp (A/B switch)
   int num_lanes = 4;
   int pair_parse = 4;     // parse units per warp for q5 / q6: 4 (default) or 2; 0 = one unit per warp (kept for A/B measurements)
   int shallow_match = 1;  // branch-free candidate scan for depth 16 / 32 (0: loop version, kept for A/B measurements)
@@ -233,6 +234,7 @@ struct B200Encoder {
     W->max_lit_trees = P.split ? 256 : 13;
     W->max_cmd_types = P.split ? 256 : 1;
     W->max_dist_types = P.split ? 256 : 1;
+    W->dist_A = (P.quality >= 10 && P.hq_split) ? BRO_DIST_A_MAX : 64u;
     W->hdr_cap = P.split ? (384u << 10) : (16u << 10);
     const bool hq = P.quality >= 10;
     if (!hq && !L.d_best.ensure(((size_t)c + 64) * 4)) return false;
@@ -259,9 +261,9 @@ struct B200Encoder {
     if (!L.d_split_counts.ensure((size_t)NM * 6 * 4)) return false;
     if (!L.d_hist_lit.ensure((size_t)NM * (W->max_lit_trees + 13) * 256 * 4)) return false;
     if (!L.d_hist_cmd.ensure((size_t)NM * (W->max_cmd_types + 1) * 704 * 4)) return false;
-    if (!L.d_hist_dist.ensure((size_t)NM * (W->max_dist_types + 1) * 64 * 4)) return false;
+    if (!L.d_hist_dist.ensure((size_t)NM * (W->max_dist_types + 1) * W->dist_A * 4)) return false;
     if (!L.d_split_codes.ensure((size_t)NM * 3 * sizeof(SplitCode))) return false;
-    const size_t code_syms = (size_t)W->max_lit_trees * 256 + (size_t)W->max_cmd_types * 704 + (size_t)W->max_dist_types * 64;
+    const size_t code_syms = (size_t)W->max_lit_trees * 256 + (size_t)W->max_cmd_types * 704 + (size_t)W->max_dist_types * W->dist_A;
     if (!L.d_codes_u8.ensure((size_t)NM * code_syms)) return false;
     if (!L.d_codes_u16.ensure((size_t)NM * code_syms * 2)) return false;
     if (!L.d_hdr.ensure((size_t)NM * W->hdr_cap)) return false;
@@ -349,12 +351,15 @@ struct B200Encoder {
     B->cap_sum = B->cap[0] + B->cap[1] + B->cap[2];
     B->maxb_sum = B->maxb[0] + B->maxb[1] + B->maxb[2];
     B->segc_sum = B->segc[0] + B->segc[1] + B->segc[2];
-    B->bh_sum = B->maxb[0] * 256 + B->maxb[1] * 704 + B->maxb[2] * 64;
+    B->dist_A = W.dist_A;
+    B->hist_stride = 100u * (256u + 704u + W.dist_A);
+    B->bh_sum = B->maxb[0] * 256 + B->maxb[1] * 704 + B->maxb[2] * W.dist_A;
     B->nsurv_stride = std::max(B->maxb[0], std::max(B->maxb[1], B->maxb[2])) / 64 + 2;
     const size_t nb = (size_t)NM * B->maxb_sum;
     if (!L.d_bs_meta.ensure((size_t)NM * 3 * sizeof(BsMeta)) || !L.d_bs_blockid.ensure((size_t)NM * B->cap_sum + 64) ||
-        !L.d_bs_signal.ensure((size_t)NM * B->cap_sum * 16 + 64) || !L.d_bs_hist.ensure((size_t)NM * 102400 * 4) ||
-        !L.d_bs_icost.ensure((size_t)NM * 102400 * 4) || !L.d_bs_first.ensure((size_t)NM * 3 * 128 * 4) || !L.d_bs_bstart.ensure((nb + NM * 3) * 4 + 64) ||
+        !L.d_bs_signal.ensure((size_t)NM * B->cap_sum * 16 + 64) || !L.d_bs_hist.ensure((size_t)NM * B->hist_stride * 4) ||
+        !L.d_bs_icost.ensure((size_t)NM * B->hist_stride * 4) || !L.d_bs_first.ensure((size_t)NM * 3 * 128 * 4) ||
+        !L.d_bs_fmap.ensure((size_t)NM * B->segc_sum * 129) || !L.d_bs_bstart.ensure((nb + NM * 3) * 4 + 64) ||
         !L.d_bs_bh_in.ensure((size_t)NM * B->bh_sum * 4) || !L.d_bs_bh_work.ensure((size_t)NM * B->bh_sum * 4) || !L.d_bs_u64.ensure(nb * 2 * 8) ||
         !L.d_bs_u32.ensure(nb * 4 * 4) || !L.d_bs_nsurv.ensure((size_t)NM * 3 * B->nsurv_stride * 4))
       return false;
@@ -364,6 +369,8 @@ struct B200Encoder {
     B->hist = L.d_bs_hist.as<uint32_t>();
     B->icost = L.d_bs_icost.as<uint32_t>();
     B->firstpos = L.d_bs_first.as<uint32_t>();
+    B->fmap = L.d_bs_fmap.as<uint8_t>();
+    B->enter = B->fmap + (size_t)NM * B->segc_sum * 128;
     B->bstart = L.d_bs_bstart.as<uint32_t>();
     B->bh_in = L.d_bs_bh_in.as<uint32_t>();
     B->bh_work = L.d_bs_bh_work.as<uint32_t>();
@@ -372,7 +379,7 @@ struct B200Encoder {
     B->csize = L.d_bs_u32.as<uint32_t>(); B->hsym = B->csize + nb; B->clusters = B->hsym + nb; B->bj = B->clusters + nb;
     B->nsurv = L.d_bs_nsurv.as<uint32_t>();
     const size_t nc = (size_t)NM * (CM_LIT_MAX + CM_DIST_MAX);
-    const size_t hl = (size_t)NM * CM_LIT_MAX * 256, hd = (size_t)NM * CM_DIST_MAX * 64;
+    const size_t hl = (size_t)NM * CM_LIT_MAX * 256, hd = (size_t)NM * CM_DIST_MAX * W.dist_A;
     if (!L.d_cm_in.ensure((hl + hd) * 4) || !L.d_cm_work.ensure((hl + hd) * 4) || !L.d_cm_u64.ensure(nc * 2 * 8) || !L.d_cm_u32.ensure(nc * 4 * 4) ||
         !L.d_cm_nsurv.ensure((size_t)NM * 2 * CM_NSURV_STRIDE * 4))
       return false;
@@ -400,7 +407,9 @@ struct B200Encoder {
     for (int it = 0; it < 3; ++it) {
       k_bs_icost<<<g3, 256, 0, st>>>(W, B);
       k_bs_forward<<<dim3(B.segc[0], NM, 3), 32, 0, st>>>(W, B);
-      k_bs_backward<<<g3, 32, 0, st>>>(W, B);
+      k_bs_bfunc<<<dim3(B.segc[0], NM, 3), 32, 0, st>>>(W, B);
+      k_bs_bchain<<<g3, 32, 0, st>>>(W, B);
+      k_bs_bwrite<<<dim3(B.segc[0], NM, 3), 32, 0, st>>>(W, B);
       k_bs_remap<<<g3, 256, 0, st>>>(W, B);
       k_bs_rehist<<<gx3, 256, 0, st>>>(W, B);
     }
@@ -420,7 +429,7 @@ struct B200Encoder {
     k_cm_cl_assign<<<gx2, CL_WARPS * 32, 0, st>>>(W, M);
     k_cm_reindex<<<g2, 256, 0, st>>>(W, M);
     k_cm_rebuild<<<gx2, 256, 0, st>>>(W, M);
-    launches += 2 + 15 + 3 + 5 + 8;
+    launches += 2 + 21 + 3 + 5 + 8;
     return true;
   }
 
@@ -544,7 +553,8 @@ struct B200Encoder {
       za.nodes = L.d_hq_nodes.as<ZNode>();
       za.pre = L.d_hq_pre.as<uint32_t>();
       za.scratch = L.d_hq_scratch.as<uint32_t>();
-      k_zopfli<<<W.num_units, 32, 0, stream>>>(W, za);
+      if (hq_thread_units) k_zopfli<<<(W.num_units + 31) / 32, 32, 0, stream>>>(W, za, 1u);
+      else k_zopfli<<<W.num_units, 32, 0, stream>>>(W, za, 32u);
     } else
     if (pair_parse == 4 && P.n_last == 4 && P.hash_type != 9)  // four units per warp (q5, q6)
       k_parse_pair<4><<<(W.num_units + 4 * PARSE_WARPS - 1) / (4 * PARSE_WARPS), PARSE_WARPS * 32, 0, stream>>>(W);
@@ -556,6 +566,12 @@ struct B200Encoder {
     k_fin_count<<<W.num_mb, 1024, 0, stream>>>(W);
     k_fin_write<<<(W.num_units + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, stream>>>(W);
     k_fin_dist<<<W.num_mb, 1024, 0, stream>>>(W);
+    if (P.quality >= 10 && P.hq_split) {  // NPOSTFIX / NDIRECT of every metablock (metablock.rs:152-207), commands re-coded
+      if (!L.d_dist_cost.ensure((size_t)W.num_mb * 64 * 8)) return false;
+      k_dist_cost<<<dim3(64, W.num_mb), 256, 0, stream>>>(W, L.d_dist_cost.as<uint64_t>());
+      k_dist_apply<<<dim3(64, W.num_mb), 256, 0, stream>>>(W, L.d_dist_cost.as<uint64_t>());
+      launches += 2;
+    }
     k_ctx_decide<<<W.num_mb, 256, 0, stream>>>(W);
     {
       dim3 g((W.cmd_cap + 255) / 256, W.num_mb);
@@ -644,6 +660,7 @@ int b200_encoder_set_option(B200Encoder* e, int option, uint32_t value) {
     case B200_OPT_PAIR_PARSE: e->pair_parse = (int)value; return 1;
     case B200_OPT_HQ_SPLIT: e->hq_split = (int)value; return 1;
     case B200_OPT_HQ_UNIT: e->hq_unit = value; return 1;
+    case B200_OPT_HQ_THREAD_UNITS: e->hq_thread_units = (int)value; return 1;
     case B200_OPT_LANES: e->num_lanes = value < 1 ? 1 : (value > (uint32_t)kMaxLanes ? kMaxLanes : (int)value); return 1;
   }
   return 0;
@@ -677,8 +694,10 @@ static bool compress_range_impl(B200Encoder* e, int quality, int lgwin, uint64_t
     done += len;
   }
   const size_t nchunks = chunks.size();
-  const cudaMemcpyKind in_kind = device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  const cudaMemcpyKind out_kind = device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  // device_io: 0 host in / host out, 1 device in / device out, 2 host in / device out, 3 device in / host out
+  const bool in_dev = device_io == 1 || device_io == 3, out_dev = device_io == 1 || device_io == 2;
+  const cudaMemcpyKind in_kind = in_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const cudaMemcpyKind out_kind = out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   if (!e->d_data.ensure(staged + kPad) || !e->d_out.ensure(need) || !e->ensure_totals(nchunks)) return false;
   e->data_base = base;
   uint8_t* dd = e->d_data.as<uint8_t>();
@@ -741,7 +760,7 @@ int b200_encoder_compress_range(B200Encoder* e, int quality, int lgwin, uint64_t
     if (first && last && n == 0) {  // encode.rs:1463-1467
       if (out_cap < 1) return 0;
       uint8_t b = 6;
-      if (device_io) { if (cudaMemcpy(out, &b, 1, cudaMemcpyHostToDevice) != cudaSuccess) return 0; }
+      if (device_io == 1 || device_io == 2) { if (cudaMemcpy(out, &b, 1, cudaMemcpyHostToDevice) != cudaSuccess) return 0; }
       else out[0] = b;
       *out_size = 1;
       return 1;

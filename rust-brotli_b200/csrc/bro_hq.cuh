@@ -125,8 +125,8 @@ BRO_HD void hq_dict_matches(const DictView& D, const uint8_t* cur, uint32_t max_
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Literal cost estimate of one unit (literal_cost.rs with the unit as the block): Q10 bits per position as exclusive
-// prefix sums pre[0..len], pre[0] = 0.  hist: scratch of 3 * 256 u32.
+// Literal cost estimate of one unit (BrotliEstimateBitCostsForLiterals, literal_cost.rs: a sliding-window histogram around every
+// position): Q10 bits per position as exclusive prefix sums pre[0..len], pre[0] = 0.  hist: scratch of 3 * 256 u32.
 // ---------------------------------------------------------------------------------------------------
 BRO_HD uint32_t hq_utf8_position(uint32_t last, uint32_t c, uint32_t clamp) {  // literal_cost.rs:8-19
   if (c < 128) return 0;
@@ -166,11 +166,16 @@ BRO_HD uint32_t hq_lit_cost_q(const uint32_t* lut, uint32_t in_window, uint32_t 
   if (ramp && i < 2000) c += 717u - ((2000u - i) * 358u) / 2000u;  // + 0.7 - (2000 - i) / 2000 * 0.35
   return c;
 }
-BRO_HD_NOINLINE void hq_literal_costs_unit(const uint8_t* d, uint32_t len, const uint32_t* lut, bool ramp, uint32_t* hist, uint32_t* pre) {
+// d = the unit's first byte; the unit is [0, len) inside the metablock span [-before, len + after): the sliding windows reach
+// into the neighbouring units (not across the metablock: its ends are where the reference's block ends are), and the start-up
+// surcharge of literal_cost.rs:173-175 applies to the first 2000 bytes of the metablock only.
+BRO_HD_NOINLINE void hq_literal_costs_unit(const uint8_t* d, uint32_t len, uint32_t before, uint32_t after, const uint32_t* lut, uint32_t* hist,
+                                           uint32_t* pre) {
   pre[0] = 0;
   if (len == 0) return;
+  const int64_t lo = -(int64_t)before, hi = (int64_t)len + after;  // metablock span relative to d
   if (hq_is_mostly_utf8(d, len)) {
-    // DecideMultiByteStatsLevel, literal_cost.rs:21-48
+    // DecideMultiByteStatsLevel, literal_cost.rs:21-48 (on the unit)
     uint32_t counts[3] = {0, 0, 0}, max_utf8 = 1, last_c = 0;
     for (uint32_t i = 0; i < len; ++i) {
       const uint32_t c = d[i];
@@ -179,47 +184,36 @@ BRO_HD_NOINLINE void hq_literal_costs_unit(const uint8_t* d, uint32_t len, const
     }
     if (counts[2] < 500) max_utf8 = 1;
     if (counts[1] + counts[2] < 25) max_utf8 = 0;
-    const uint32_t window_half = 495;
-    const uint32_t in_window = bmin(window_half, len);
+    const int64_t W = 495;
     uint32_t in_window_utf8[3] = {0, 0, 0};
     for (uint32_t i = 0; i < 3 * 256; ++i) hist[i] = 0;
-    {
-      uint32_t lc = 0, up = 0;
-      for (uint32_t i = 0; i < in_window; ++i) {
-        const uint32_t c = d[i];
-        ++hist[up * 256 + c];
-        ++in_window_utf8[up];
-        up = hq_utf8_position(lc, c, max_utf8);
-        lc = c;
-      }
-    }
+    auto cls = [&](int64_t p) -> uint32_t {  // class of the byte at p from its two predecessors (0 outside the metablock)
+      const uint32_t c = p - 1 >= lo ? d[p - 1] : 0u, lc = p - 2 >= lo ? d[p - 2] : 0u;
+      return hq_utf8_position(lc, c, max_utf8);
+    };
+    // window of position 0: [max(lo, -W), min(hi, W))
+    for (int64_t p = (-W > lo ? -W : lo); p < (W < hi ? W : hi); ++p) { const uint32_t k = cls(p); ++hist[k * 256 + d[p]]; ++in_window_utf8[k]; }
     for (uint32_t i = 0; i < len; ++i) {
-      if (i >= window_half) {
-        const uint32_t c = i < window_half + 1 ? 0u : d[i - window_half - 1];
-        const uint32_t lc = i < window_half + 2 ? 0u : d[i - window_half - 2];
-        const uint32_t up2 = hq_utf8_position(lc, c, max_utf8);
-        --hist[up2 * 256 + d[i - window_half]];
-        --in_window_utf8[up2];
+      const int64_t out = (int64_t)i - W - 1, in = (int64_t)i + W - 1;  // window of i: [i - W, i + W)
+      if (i > 0) {
+        if (out >= lo) { const uint32_t k = cls(out); --hist[k * 256 + d[out]]; --in_window_utf8[k]; }
+        if (in < hi) { const uint32_t k = cls(in); ++hist[k * 256 + d[in]]; ++in_window_utf8[k]; }
       }
-      if (i + window_half < len) {
-        const uint32_t c = d[i + window_half - 1], lc = d[i + window_half - 2];
-        const uint32_t up2 = hq_utf8_position(lc, c, max_utf8);
-        ++hist[up2 * 256 + d[i + window_half]];
-        ++in_window_utf8[up2];
-      }
-      const uint32_t c = i < 1 ? 0u : d[i - 1], lc = i < 2 ? 0u : d[i - 2];
-      const uint32_t up = hq_utf8_position(lc, c, max_utf8);
-      pre[i + 1] = pre[i] + hq_lit_cost_q(lut, in_window_utf8[up], hist[up * 256 + d[i]], i, ramp);
+      const uint32_t up = cls((int64_t)i);
+      pre[i + 1] = pre[i] + hq_lit_cost_q(lut, in_window_utf8[up], hist[up * 256 + d[i]], before + i, true);
     }
   } else {
-    const uint32_t window_half = 2000;
-    uint32_t in_window = bmin(window_half, len);
+    const int64_t W = 2000;
+    uint32_t in_window = 0;
     for (uint32_t i = 0; i < 256; ++i) hist[i] = 0;
-    for (uint32_t i = 0; i < in_window; ++i) ++hist[d[i]];
+    for (int64_t p = (-W > lo ? -W : lo); p < (W < hi ? W : hi); ++p) { ++hist[d[p]]; ++in_window; }
     for (uint32_t i = 0; i < len; ++i) {
-      if (i >= window_half) { --hist[d[i - window_half]]; --in_window; }
-      if (i + window_half < len) { ++hist[d[i + window_half]]; ++in_window; }
-      pre[i + 1] = pre[i] + hq_lit_cost_q(lut, in_window, hist[d[i]], i, ramp);
+      const int64_t out = (int64_t)i - W - 1, in = (int64_t)i + W - 1;
+      if (i > 0) {
+        if (out >= lo) { --hist[d[out]]; --in_window; }
+        if (in < hi) { ++hist[d[in]]; ++in_window; }
+      }
+      pre[i + 1] = pre[i] + hq_lit_cost_q(lut, in_window, hist[d[i]], before + i, true);
     }
   }
 }

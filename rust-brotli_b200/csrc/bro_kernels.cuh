@@ -37,7 +37,7 @@ struct MBDesc {
   uint32_t hdr_bits;
   uint32_t raw;               // stored uncompressed
   uint32_t has_long;          // some command has more than LONG_INS literals
-  uint32_t pad_;
+  uint32_t dist_params;       // NPOSTFIX | NDIRECT << 8 (0 below quality 10)
   uint64_t body_bits;
   uint64_t out_bitpos;        // position of the metablock in the output stream
 };
@@ -85,6 +85,7 @@ struct Workspace {
   // splits: capacities per metablock
   uint32_t lit_blk_cap, cmd_blk_cap, dist_blk_cap;
   uint32_t max_lit_trees, max_cmd_types, max_dist_types;
+  uint32_t dist_A;         // width of a distance histogram / code table: 64, or BRO_DIST_A_MAX when NPOSTFIX / NDIRECT are searched
   uint8_t *lit_types, *cmd_types, *dist_types;
   uint32_t *lit_lengths, *cmd_lengths, *dist_lengths;
   uint32_t *lit_starts, *cmd_starts, *dist_starts;
@@ -135,7 +136,8 @@ __device__ __forceinline__ MetaCodes make_codes(const Workspace& W, uint32_t m) 
   mc.lit_sc = W.split_codes + (size_t)m * 3; mc.cmd_sc = mc.lit_sc + 1; mc.dist_sc = mc.lit_sc + 2;
   mc.lit_depth = W.lit_depth + (size_t)m * W.max_lit_trees * 256; mc.lit_code = W.lit_code + (size_t)m * W.max_lit_trees * 256;
   mc.cmd_depth = W.cmd_depth + (size_t)m * W.max_cmd_types * 704; mc.cmd_code = W.cmd_code + (size_t)m * W.max_cmd_types * 704;
-  mc.dist_depth = W.dist_depth + (size_t)m * W.max_dist_types * 64; mc.dist_code = W.dist_code + (size_t)m * W.max_dist_types * 64;
+  mc.dist_depth = W.dist_depth + (size_t)m * W.max_dist_types * W.dist_A; mc.dist_code = W.dist_code + (size_t)m * W.max_dist_types * W.dist_A;
+  mc.dist_A = W.dist_A;
   mc.ctx_map_id = W.mb[m].ctx_map_id;
   mc.nctx = ctxmap_num_contexts(mc.ctx_map_id);
   const bool full = mc.ctx_map_id >= CTXMAP_FULL_UTF8;  // quality >= 10: clustered context maps
@@ -1757,11 +1759,11 @@ __device__ __forceinline__ CatInfo cat_info(const Workspace& W, uint32_t m, int 
     c.starts = W.cmd_starts + (size_t)m * W.cmd_blk_cap;
     c.hist = W.cmd_hist + (size_t)m * (W.max_cmd_types + 1) * 704; c.counts = W.split_counts + (size_t)m * 6 + 2;
   } else {
-    c.syms = W.dist_syms + (size_t)m * W.cmd_cap; c.count = mb.ndist; c.A = 64; c.nctx = 1;
+    c.syms = W.dist_syms + (size_t)m * W.cmd_cap; c.count = mb.ndist; c.A = W.dist_A; c.nctx = 1;
     c.min_block = 512; c.thr_bits = 100; c.max_types = 256;
     c.types = W.dist_types + (size_t)m * W.dist_blk_cap; c.lengths = W.dist_lengths + (size_t)m * W.dist_blk_cap;
     c.starts = W.dist_starts + (size_t)m * W.dist_blk_cap;
-    c.hist = W.dist_hist + (size_t)m * (W.max_dist_types + 1) * 64; c.counts = W.split_counts + (size_t)m * 6 + 4;
+    c.hist = W.dist_hist + (size_t)m * (W.max_dist_types + 1) * W.dist_A; c.counts = W.split_counts + (size_t)m * 6 + 4;
   }
   if (c.max_types > (cat == 0 ? W.max_lit_trees / c.nctx : (cat == 1 ? W.max_cmd_types : W.max_dist_types)))
     c.max_types = (cat == 0 ? W.max_lit_trees / c.nctx : (cat == 1 ? W.max_cmd_types : W.max_dist_types));
@@ -2029,7 +2031,7 @@ __global__ void __launch_bounds__(32) k_trees(Workspace W) {
   }
   if (t >= nlit + ncmd + ndist) return;
   const uint32_t slot = t;
-  uint32_t* hist; uint8_t* depth; uint16_t* code; uint32_t A;
+  uint32_t* hist; uint8_t* depth; uint16_t* code; uint32_t A, alphabet = 0;
   if (t < nlit) {
     A = 256; hist = W.lit_hist + ((size_t)m * (W.max_lit_trees + 13) + t) * 256;
     depth = W.lit_depth + ((size_t)m * W.max_lit_trees + t) * 256; code = W.lit_code + ((size_t)m * W.max_lit_trees + t) * 256;
@@ -2037,8 +2039,9 @@ __global__ void __launch_bounds__(32) k_trees(Workspace W) {
     t -= nlit; A = 704; hist = W.cmd_hist + ((size_t)m * (W.max_cmd_types + 1) + t) * 704;
     depth = W.cmd_depth + ((size_t)m * W.max_cmd_types + t) * 704; code = W.cmd_code + ((size_t)m * W.max_cmd_types + t) * 704;
   } else {
-    t -= nlit + ncmd; A = 64; hist = W.dist_hist + ((size_t)m * (W.max_dist_types + 1) + t) * 64;
-    depth = W.dist_depth + ((size_t)m * W.max_dist_types + t) * 64; code = W.dist_code + ((size_t)m * W.max_dist_types + t) * 64;
+    t -= nlit + ncmd; A = W.dist_A; hist = W.dist_hist + ((size_t)m * (W.max_dist_types + 1) + t) * A;
+    depth = W.dist_depth + ((size_t)m * W.max_dist_types + t) * A; code = W.dist_code + ((size_t)m * W.max_dist_types + t) * A;
+    alphabet = distance_alphabet_size(mb.dist_params & 0xFFu, mb.dist_params >> 8);  // symbol width of the simple / one-symbol forms
   }
   const uint32_t tree_cap = W.max_lit_trees + W.max_cmd_types + W.max_dist_types;
   // == huff_build_and_store() with the sort done by the whole warp; everything is worked on in shared memory: the merge, the
@@ -2048,7 +2051,7 @@ __global__ void __launch_bounds__(32) k_trees(Workspace W) {
   if (P.use_rle_opt && lane == 0) huff_smooth_counts(A, s_hist);
   __syncwarp();
   uint32_t max_bits = 0;
-  for (uint32_t c = A - 1; c; c >>= 1) ++max_bits;
+  for (uint32_t c = (alphabet ? alphabet : A) - 1; c; c >>= 1) ++max_bits;
   const uint32_t used = huff_sorted_keys_warp(s_hist, A, ws_s.key);
   BitWriter bw;
   bw.init(W.tree_bits + ((size_t)m * tree_cap + slot) * TREE_SLOT_BYTES);
@@ -2112,8 +2115,8 @@ __global__ void __launch_bounds__(32) k_header(Workspace W) {
     const uint8_t* sect = W.sect_bits + (size_t)m * HDR_SECTIONS * SECT_BYTES;
     const uint32_t* snb = W.sect_nbits + (size_t)m * HDR_SECTIONS;
     for (uint32_t k = 0; k < 3; ++k) append_bits(bw, sect + (size_t)k * SECT_BYTES, snb[k]);  // block-split codes
-    bw.put(2, 0);
-    bw.put(4, 0);
+    bw.put(2, mb.dist_params & 0xFFu);                               // NPOSTFIX
+    bw.put(4, (mb.dist_params >> 8) >> (mb.dist_params & 0xFFu));    // NDIRECT >> NPOSTFIX
     for (uint32_t i = 0; i < lv.num_types; ++i) bw.put(2, mb.ctx_map_id == CTXMAP_FULL_SIGNED ? 3 : 2);  // CONTEXT_SIGNED / CONTEXT_UTF8
     append_bits(bw, sect + (size_t)3 * SECT_BYTES, snb[3]);  // literal context map
     append_bits(bw, sect + (size_t)4 * SECT_BYTES, snb[4]);  // distance context map

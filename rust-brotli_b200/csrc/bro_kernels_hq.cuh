@@ -90,9 +90,11 @@ struct ZopfliArgs {
   uint32_t* scratch;  // [num_units][HQ_SCRATCH_WORDS]
 };
 
-__global__ void __launch_bounds__(32) k_zopfli(Workspace W, ZopfliArgs Z) {
-  const uint32_t u = blockIdx.x;
-  if (u >= W.num_units || threadIdx.x != 0) return;
+// lanes_per_unit = 32: one unit per warp (lane 0 works); 1: one unit per thread (32 units per warp: the lanes diverge, but the hot
+// loops -- byte compares, per-length cost updates -- reconverge often enough to beat 31 idle lanes)
+__global__ void __launch_bounds__(32) k_zopfli(Workspace W, ZopfliArgs Z, uint32_t lanes_per_unit) {
+  const uint32_t u = lanes_per_unit == 1 ? blockIdx.x * 32 + threadIdx.x : blockIdx.x;
+  if (u >= W.num_units || (lanes_per_unit != 1 && threadIdx.x != 0)) return;
   const EncParams& P = W.P;
   const uint32_t s = u * P.unit, e = bmin(P.n, s + P.unit);
   uint32_t* scr = Z.scratch + (size_t)u * HQ_SCRATCH_WORDS;
@@ -106,7 +108,10 @@ __global__ void __launch_bounds__(32) k_zopfli(Workspace W, ZopfliArgs Z) {
   U.data = W.data; U.ustart = s; U.len = e - s; U.abs_base = P.abs_base; U.max_backward = P.max_backward; U.quality = P.quality;
   U.model = model; U.lit_pre = pre; U.start_dc = start_dc; U.nodes = Z.nodes + (size_t)u * (P.unit + 1);
   hq_model_initial(model, W.lut);
-  hq_literal_costs_unit(W.data + s, U.len, W.lut, true, hist, pre);
+  {
+    const uint32_t mb_span = P.unit * P.mb_units, mb_lo = s / mb_span * mb_span, mb_hi = bmin(P.n, mb_lo + mb_span);
+    hq_literal_costs_unit(W.data + s, U.len, s - mb_lo, mb_hi - e, W.lut, hist, pre);
+  }
   RawCmd* out = W.raw + (size_t)u * (P.unit / 2 + 1);
   const bool two = P.quality >= 11;
   uint32_t tail, ncopy, ncmd;
@@ -410,13 +415,16 @@ struct BsMeta {
 };
 struct BsWs {  // device view of one lane's block-split workspace; every array is [num_mb][...] with the three categories side by side
   uint32_t cap[3], maxb[3], segc[3];   // per-category capacities: symbols, blocks, segments
-  uint32_t cap_sum, maxb_sum, segc_sum, bh_sum;  // bh_sum = maxb0 * 256 + maxb1 * 704 + maxb2 * 64
+  uint32_t cap_sum, maxb_sum, segc_sum, bh_sum;  // bh_sum = maxb0 * 256 + maxb1 * 704 + maxb2 * dist_A
+  uint32_t dist_A, hist_stride;                  // hist_stride = 100 * (256 + 704 + dist_A)
   BsMeta* meta;          // [num_mb][3]
   uint8_t* blockid;      // [num_mb][cap_sum]
   uint32_t* signal;      // [num_mb][cap_sum][4]
   uint32_t* hist;        // [num_mb][100 * 1024]
   uint32_t* icost;       // [num_mb][100 * 1024]
   uint32_t* firstpos;    // [num_mb][3][128]
+  uint8_t* fmap;         // [num_mb][segc_sum][128]  backward map of every segment
+  uint8_t* enter;        // [num_mb][segc_sum]       id at the first symbol behind the segment
   uint32_t* bstart;      // [num_mb][maxb_sum]  first symbol of each block (+ nb: count)
   uint32_t* bh_in;       // [num_mb][bh_sum]    block histograms
   uint32_t* bh_work;     // [num_mb][bh_sum]
@@ -427,8 +435,8 @@ struct BsWs {  // device view of one lane's block-split workspace; every array i
   uint32_t nsurv_stride;
 };
 __device__ __forceinline__ uint32_t bs_off(const uint32_t* v, int cat) { return cat == 0 ? 0u : (cat == 1 ? v[0] : v[0] + v[1]); }
-__device__ __forceinline__ uint32_t bs_bh_off(const BsWs& B, int cat) { return cat == 0 ? 0u : (cat == 1 ? B.maxb[0] * 256u : B.maxb[0] * 256u + B.maxb[1] * 704u); }
-__device__ __forceinline__ uint32_t bs_hist_off(int cat) { return cat == 0 ? 0u : (cat == 1 ? 100u * 256u : 100u * 256u + 100u * 704u); }
+__device__ __forceinline__ uint32_t bs_bh_off(const BsWs& B, int cat) { return cat == 0 ? 0u : (cat == 1 ? B.maxb[0] * 256u : B.maxb[0] * 256u + B.maxb[1] * 704u); }  // (the distance part is last)
+__device__ __forceinline__ uint32_t bs_hist_off(int cat) { return cat == 0 ? 0u : (cat == 1 ? 100u * 256u : 100u * 256u + 100u * 704u); }  // (the distance part is last)
 
 struct BsCat {  // one (metablock, category) problem
   const uint16_t* syms;
@@ -445,15 +453,15 @@ struct BsCat {  // one (metablock, category) problem
 __device__ __forceinline__ BsCat bs_cat(const Workspace& W, const BsWs& B, uint32_t m, int cat) {
   BsCat c;
   const MBDesc& mb = W.mb[m];
-  c.p = bs_params(cat);
+  c.p = bs_params(cat, B.dist_A);
   if (cat == 0) { c.syms = W.lit_syms + mb.start; c.mask = 0xFFu; }
   else if (cat == 1) { c.syms = W.cmd_syms + (size_t)m * W.cmd_cap; c.mask = 0x3FFu; }
   else { c.syms = W.dist_syms + (size_t)m * W.cmd_cap; c.mask = 0x3FFu; }
   c.meta = B.meta + (size_t)m * 3 + cat;
   c.blockid = B.blockid + (size_t)m * B.cap_sum + bs_off(B.cap, cat);
   c.signal = B.signal + ((size_t)m * B.cap_sum + bs_off(B.cap, cat)) * 4;
-  c.hist = B.hist + (size_t)m * 102400 + bs_hist_off(cat);
-  c.icost = B.icost + (size_t)m * 102400 + bs_hist_off(cat);
+  c.hist = B.hist + (size_t)m * B.hist_stride + bs_hist_off(cat);
+  c.icost = B.icost + (size_t)m * B.hist_stride + bs_hist_off(cat);
   c.firstpos = B.firstpos + ((size_t)m * 3 + cat) * 128;
   c.bstart = B.bstart + (size_t)m * B.maxb_sum + bs_off(B.maxb, cat);
   c.maxb = B.maxb[cat];
@@ -462,7 +470,7 @@ __device__ __forceinline__ BsCat bs_cat(const Workspace& W, const BsWs& B, uint3
 __device__ __forceinline__ ClProblem bs_cluster_problem(const Workspace& W, const BsWs& B, uint32_t m, int cat) {
   ClProblem C;
   const size_t bo = (size_t)m * B.maxb_sum + bs_off(B.maxb, cat);
-  C.A = bs_params(cat).A;
+  C.A = bs_params(cat, B.dist_A).A;
   C.n = B.meta[(size_t)m * 3 + cat].nb;
   C.in = B.bh_in + (size_t)m * B.bh_sum + bs_bh_off(B, cat);
   C.work = B.bh_work + (size_t)m * B.bh_sum + bs_bh_off(B, cat);
@@ -569,9 +577,59 @@ __global__ void __launch_bounds__(32) k_bs_forward(Workspace W, BsWs B) {
     }
   }
 }
-// Backward pass of FindBlocks (block_splitter.rs:323-347): the exact sequential rule over the recorded switch bits, one thread
-// per (metablock, category).  grid (num_mb, 3), 32 threads.
-__global__ void __launch_bounds__(32) k_bs_backward(Workspace W, BsWs B) {
+// Backward pass of FindBlocks (block_splitter.rs:323-347), exact but segment parallel.  The id at symbol i is a function of the id
+// at i + 1 (keep it, or jump to the cheapest code of i when the switch bit of the kept id is set), so a segment is a map
+// "id at the first symbol behind the segment -> id at its first symbol":
+//   k_bs_bfunc   one warp per segment walks all 128 hypotheses at once (4 per lane); they usually coalesce after a few hundred
+//                symbols, from where on a single walk is enough;
+//   k_bs_bchain  one thread per (metablock, category) chains the maps from the last segment to the first;
+//   k_bs_bwrite  one lane per segment repeats its walk with the now known incoming id and writes the ids.
+__global__ void __launch_bounds__(32) k_bs_bfunc(Workspace W, BsWs B) {
+  const uint32_t m = blockIdx.y;
+  const int cat = (int)blockIdx.z;
+  const BsCat c = bs_cat(W, B, m, cat);
+  const BsMeta t = *c.meta;
+  if (t.simple || t.nh <= 1 || blockIdx.x >= t.nseg) return;
+  const uint32_t lane = threadIdx.x;
+  const uint32_t s = blockIdx.x * BS_SEG, e = bmin(t.count, s + BS_SEG);
+  uint32_t cur[4] = {lane, lane + 32, lane + 64, lane + 96};
+  uint32_t hi = e;
+  bool uniform = false;
+  if (e == t.count) {  // the last symbol keeps its own cheapest code whatever comes in
+    const uint32_t last = c.blockid[t.count - 1];
+    cur[0] = cur[1] = cur[2] = cur[3] = last;
+    hi = t.count - 1;
+    uniform = true;
+  }
+  for (uint32_t i = hi; i > s;) {
+    --i;
+    const uint4 sg = *reinterpret_cast<const uint4*>(c.signal + (size_t)i * 4);
+    const uint32_t bid = c.blockid[i];
+    if (uniform) {
+      const uint32_t x = cur[0];
+      const uint32_t word = (x >> 5) == 0 ? sg.x : ((x >> 5) == 1 ? sg.y : ((x >> 5) == 2 ? sg.z : sg.w));
+      if (((word >> (x & 31)) & 1u) && x != bid) cur[0] = bid;
+      continue;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t x = cur[q];
+      const uint32_t word = (x >> 5) == 0 ? sg.x : ((x >> 5) == 1 ? sg.y : ((x >> 5) == 2 ? sg.z : sg.w));
+      if (((word >> (x & 31)) & 1u) && x != bid) cur[q] = bid;
+    }
+    if ((i & 15u) == 0) {  // all hypotheses below nh agree: one walk from here on
+      const uint32_t c0 = __shfl_sync(FULLMASK, cur[0], 0);
+      const bool same = (lane >= t.nh || cur[0] == c0) && (lane + 32 >= t.nh || cur[1] == c0) && (lane + 64 >= t.nh || cur[2] == c0) &&
+                        (lane + 96 >= t.nh || cur[3] == c0);
+      if (__all_sync(FULLMASK, same)) { uniform = true; cur[0] = c0; }
+    }
+  }
+  uint8_t* f = B.fmap + ((size_t)m * B.segc_sum + bs_off(B.segc, cat) + blockIdx.x) * 128;
+  if (uniform) { const uint8_t v = (uint8_t)cur[0]; f[lane] = v; f[lane + 32] = v; f[lane + 64] = v; f[lane + 96] = v; }
+  else { f[lane] = (uint8_t)cur[0]; f[lane + 32] = (uint8_t)cur[1]; f[lane + 64] = (uint8_t)cur[2]; f[lane + 96] = (uint8_t)cur[3]; }
+}
+// grid (num_mb, 3), 32 threads
+__global__ void __launch_bounds__(32) k_bs_bchain(Workspace W, BsWs B) {
   const uint32_t m = blockIdx.x;
   const int cat = (int)blockIdx.y;
   const BsCat c = bs_cat(W, B, m, cat);
@@ -582,8 +640,26 @@ __global__ void __launch_bounds__(32) k_bs_backward(Workspace W, BsWs B) {
     return;
   }
   if (threadIdx.x != 0) return;
-  uint32_t cur = c.blockid[t.count - 1];
-  for (uint32_t i = t.count - 1; i > 0;) {
+  const uint8_t* fmap = B.fmap + ((size_t)m * B.segc_sum + bs_off(B.segc, cat)) * 128;
+  uint8_t* enter = B.enter + (size_t)m * B.segc_sum + bs_off(B.segc, cat);
+  uint32_t id = 0;  // the last segment ignores its incoming id
+  for (uint32_t sgm = t.nseg; sgm-- > 0;) {
+    enter[sgm] = (uint8_t)id;
+    id = fmap[(size_t)sgm * 128 + id];
+  }
+}
+// grid (segments, num_mb, 3), 32 threads (lane 0 works)
+__global__ void __launch_bounds__(32) k_bs_bwrite(Workspace W, BsWs B) {
+  const uint32_t m = blockIdx.y;
+  const int cat = (int)blockIdx.z;
+  const BsCat c = bs_cat(W, B, m, cat);
+  const BsMeta t = *c.meta;
+  if (t.simple || t.nh <= 1 || blockIdx.x >= t.nseg || threadIdx.x != 0) return;
+  const uint32_t s = blockIdx.x * BS_SEG, e = bmin(t.count, s + BS_SEG);
+  uint32_t cur = B.enter[(size_t)m * B.segc_sum + bs_off(B.segc, cat) + blockIdx.x];
+  uint32_t hi = e;
+  if (e == t.count) { cur = c.blockid[t.count - 1]; hi = t.count - 1; }
+  for (uint32_t i = hi; i > s;) {
     --i;
     const uint32_t word = c.signal[(size_t)i * 4 + (cur >> 5)];
     const uint32_t bid = c.blockid[i];
@@ -771,6 +847,57 @@ __global__ void __launch_bounds__(32) k_bs_types(Workspace W, BsWs B) {
 namespace bro {
 
 // ===================================================================================================
+// Distance alphabet parameters (BrotliBuildMetaBlock + ComputeDistanceCost, metablock.rs:88-207): the cost of all 64 (NPOSTFIX,
+// NDIRECT) combinations in parallel -- one CTA per combination and metablock re-codes every distance, histograms the symbols in
+// shared memory and sums the extra bits -- then the reference's greedy walk over the table, then the commands are re-coded.
+// ===================================================================================================
+__global__ void __launch_bounds__(256) k_dist_cost(Workspace W, uint64_t* cost /* [num_mb][64] */) {
+  __shared__ uint32_t s_h[BRO_DIST_A_MAX];
+  __shared__ uint32_t s_dh[18];
+  __shared__ unsigned long long s_extra;
+  const uint32_t m = blockIdx.y, np = blockIdx.x >> 4, nd = (blockIdx.x & 15u) << np;
+  const MBDesc& mb = W.mb[m];
+  for (uint32_t i = threadIdx.x; i < BRO_DIST_A_MAX; i += blockDim.x) s_h[i] = 0;
+  if (threadIdx.x == 0) s_extra = 0;
+  __syncthreads();
+  uint32_t extra_bits = 0;
+  const GCmd* cmds = W.cmds + (size_t)m * W.cmd_cap;
+  for (uint32_t i = threadIdx.x; i < mb.ncmd; i += blockDim.x) {
+    const GCmd g = cmds[i];
+    if (g.copy_len == 0 || g.cmd_prefix < 128) continue;
+    uint32_t sn, ex;
+    prefix_encode_copy_distance_params(restore_distance_code00(g.dist_prefix, g.dist_extra), np, nd, &sn, &ex);
+    atomicAdd(&s_h[sn & 0x3ffu], 1u);
+    extra_bits += sn >> 10;
+  }
+  extra_bits = warp_sum_u32(extra_bits);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_extra, (unsigned long long)extra_bits);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const uint64_t pc = warp_pop_cost(s_h, nullptr, BRO_DIST_A_MAX, W.lut, s_dh);
+    if (threadIdx.x == 0) cost[(size_t)m * 64 + blockIdx.x] = pc + ((uint64_t)s_extra << 16);
+  }
+}
+// grid (x, num_mb): every CTA repeats the (tiny) decision, CTA 0 records it, all re-code their share of the commands
+__global__ void __launch_bounds__(256) k_dist_apply(Workspace W, const uint64_t* cost) {
+  const uint32_t m = blockIdx.y;
+  MBDesc& mb = W.mb[m];
+  const uint32_t ch = choose_distance_params(cost + (size_t)m * 64);
+  const uint32_t np = ch & 0xFFu, nd = ch >> 8;
+  if (blockIdx.x == 0 && threadIdx.x == 0) mb.dist_params = ch;
+  if (ch == 0) return;
+  GCmd* cmds = W.cmds + (size_t)m * W.cmd_cap;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < mb.ncmd; i += gridDim.x * blockDim.x) {
+    GCmd& g = cmds[i];
+    if (g.copy_len == 0 || g.cmd_prefix < 128) continue;
+    uint32_t sn, ex;
+    prefix_encode_copy_distance_params(restore_distance_code00(g.dist_prefix, g.dist_extra), np, nd, &sn, &ex);
+    g.dist_prefix = (uint16_t)sn;
+    g.dist_extra = ex;
+  }
+}
+
+// ===================================================================================================
 // Context maps (BrotliBuildMetaBlock, metablock.rs:133-301): histograms per (block type, context), clustered to at most 256
 // prefix codes per category; the clusters' histograms are the coding histograms, the assignment is the context map.
 // ===================================================================================================
@@ -793,7 +920,7 @@ __device__ ClProblem cm_cluster_problem(const Workspace& W, const CmWs& M, uint3
   const uint32_t* cnt = W.split_counts + (size_t)m * 6;
   const size_t po = (size_t)m * (CM_LIT_MAX + CM_DIST_MAX) + (which ? CM_LIT_MAX : 0u);
   if (which == 0) { C.A = 256; C.n = cnt[1] * 64u; C.in = M.in_lit + (size_t)m * CM_LIT_MAX * 256; C.work = M.work_lit + (size_t)m * CM_LIT_MAX * 256; }
-  else { C.A = 64; C.n = cnt[5] * 4u; C.in = M.in_dist + (size_t)m * CM_DIST_MAX * 64; C.work = M.work_dist + (size_t)m * CM_DIST_MAX * 64; }
+  else { C.A = W.dist_A; C.n = cnt[5] * 4u; C.in = M.in_dist + (size_t)m * CM_DIST_MAX * W.dist_A; C.work = M.work_dist + (size_t)m * CM_DIST_MAX * W.dist_A; }
   C.cost = M.cost + po; C.size = M.size + po; C.sym = M.sym + po; C.clusters = M.clusters + po; C.bj = M.bj + po; C.bd = M.bd + po;
   C.nsurv = M.nsurv + ((size_t)m * 2 + which) * CM_NSURV_STRIDE + 1;
   C.batch_max = 256;
@@ -804,9 +931,9 @@ __device__ ClProblem cm_cluster_problem(const Workspace& W, const CmWs& M, uint3
 __global__ void __launch_bounds__(256) k_cm_zero(Workspace W, CmWs M) {
   const uint32_t m = blockIdx.y;
   const uint32_t* cnt = W.split_counts + (size_t)m * 6;
-  const size_t nl = (size_t)cnt[1] * 64 * 256, nd = (size_t)cnt[5] * 4 * 64, nc = (size_t)cnt[3] * 704;
+  const size_t nl = (size_t)cnt[1] * 64 * 256, nd = (size_t)cnt[5] * 4 * W.dist_A, nc = (size_t)cnt[3] * 704;
   uint32_t* il = M.in_lit + (size_t)m * CM_LIT_MAX * 256;
-  uint32_t* id = M.in_dist + (size_t)m * CM_DIST_MAX * 64;
+  uint32_t* id = M.in_dist + (size_t)m * CM_DIST_MAX * W.dist_A;
   uint32_t* ch = W.cmd_hist + (size_t)m * (W.max_cmd_types + 1) * 704;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nl + nd + nc; i += (size_t)gridDim.x * blockDim.x) {
     if (i < nl) il[i] = 0;
@@ -823,14 +950,14 @@ __global__ void __launch_bounds__(256) k_cm_hist(Workspace W, CmWs M) {
   const uint32_t count = cat == 0 ? mb.nlit : (cat == 1 ? mb.ncmd : mb.ndist);
   const uint16_t* syms = cat == 0 ? W.lit_syms + mb.start : (cat == 1 ? W.cmd_syms + (size_t)m * W.cmd_cap : W.dist_syms + (size_t)m * W.cmd_cap);
   uint32_t* il = M.in_lit + (size_t)m * CM_LIT_MAX * 256;
-  uint32_t* id = M.in_dist + (size_t)m * CM_DIST_MAX * 64;
+  uint32_t* id = M.in_dist + (size_t)m * CM_DIST_MAX * W.dist_A;
   uint32_t* ch = W.cmd_hist + (size_t)m * (W.max_cmd_types + 1) * 704;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
     const uint32_t t = v.types[v.num_blocks > 1 ? find_block(v.starts, v.num_blocks, i) : 0u];
     const uint32_t s = syms[i];
     if (cat == 0) atomicAdd(&il[((size_t)t * 64 + (s >> 8)) * 256 + (s & 0xFFu)], 1u);
     else if (cat == 1) atomicAdd(&ch[(size_t)t * 704 + s], 1u);
-    else atomicAdd(&id[((size_t)t * 4 + (s >> 10)) * 64 + (s & 0x3FFu)], 1u);
+    else atomicAdd(&id[((size_t)t * 4 + (s >> 10)) * W.dist_A + (s & 0x3FFu)], 1u);
   }
 }
 __global__ void __launch_bounds__(CL_WARPS * 32) k_cm_cl_prepare(Workspace W, CmWs M) {
@@ -878,7 +1005,7 @@ __global__ void __launch_bounds__(256) k_cm_reindex(Workspace W, CmWs M) {
   uint8_t* cmap = which == 0 ? M.lit_cmap + (size_t)m * CM_LIT_MAX : M.dist_cmap + (size_t)m * CM_DIST_MAX;
   const bool replicate = which == 0 && !W.P.ctx_model;  // literal context modelling off: every context uses the code of context 0
   for (uint32_t i = threadIdx.x; i < C.n; i += blockDim.x) cmap[i] = (uint8_t)new_index[C.sym[replicate ? (i & ~63u) : i]];
-  uint32_t* out = which == 0 ? W.lit_hist + (size_t)m * (W.max_lit_trees + 13) * 256 : W.dist_hist + (size_t)m * (W.max_dist_types + 1) * 64;
+  uint32_t* out = which == 0 ? W.lit_hist + (size_t)m * (W.max_lit_trees + 13) * 256 : W.dist_hist + (size_t)m * (W.max_dist_types + 1) * W.dist_A;
   for (uint32_t i = threadIdx.x; i < s_next * C.A; i += blockDim.x) out[i] = 0;
 }
 // output histogram of a code = sum of the inputs mapped to it.  grid (x, num_mb, 2)
@@ -887,7 +1014,7 @@ __global__ void __launch_bounds__(256) k_cm_rebuild(Workspace W, CmWs M) {
   const int which = (int)blockIdx.z;
   const ClProblem C = cm_cluster_problem(W, M, m, which);
   const uint8_t* cmap = which == 0 ? M.lit_cmap + (size_t)m * CM_LIT_MAX : M.dist_cmap + (size_t)m * CM_DIST_MAX;
-  uint32_t* out = which == 0 ? W.lit_hist + (size_t)m * (W.max_lit_trees + 13) * 256 : W.dist_hist + (size_t)m * (W.max_dist_types + 1) * 64;
+  uint32_t* out = which == 0 ? W.lit_hist + (size_t)m * (W.max_lit_trees + 13) * 256 : W.dist_hist + (size_t)m * (W.max_dist_types + 1) * W.dist_A;
   const size_t total = (size_t)C.n * C.A;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const uint32_t v = C.in[i];

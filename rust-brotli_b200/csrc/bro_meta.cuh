@@ -271,6 +271,7 @@ struct MetaCodes {
   // quality >= 10 (ctx_map_id >= CTXMAP_FULL_UTF8): clustered context maps, entries are prefix-code indices
   const uint8_t* lit_cmap;    // [lit types][64]
   const uint8_t* dist_cmap;   // [dist types][4], null = one code per distance block type
+  uint32_t dist_A;            // width of a distance code table: 64, or BRO_DIST_A_MAX when NPOSTFIX / NDIRECT are searched
 };
 BRO_HD uint32_t literal_tree(const MetaCodes& mc, uint32_t type, uint8_t p1, uint8_t p2) {
   if (mc.ctx_map_id >= CTXMAP_FULL_UTF8) return mc.lit_cmap[type * 64u + literal_context(mc.ctx_map_id, p1, p2)];
@@ -368,7 +369,7 @@ BRO_HD_NOINLINE void emit_command(W& w, const MetaCodes& mc, const Cmd& c, uint3
     uint32_t t = mc.dist.types[b];
     if (mc.dist_cmap) t = mc.dist_cmap[t * 4u + distance_context(c.cmd_prefix)];
     uint32_t sym = c.dist_prefix & 0x3ffu;
-    w.put(mc.dist_depth[t * 64 + sym], mc.dist_code[t * 64 + sym]);
+    w.put(mc.dist_depth[t * mc.dist_A + sym], mc.dist_code[t * mc.dist_A + sym]);
     w.put(c.dist_prefix >> 10, c.dist_extra);
   }
 }
