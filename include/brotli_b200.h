@@ -136,6 +136,9 @@ int b200_device_count(void);
 int b200_effective_quality(int requested_quality);
 B200Encoder* b200_encoder_create(int device);
 void b200_encoder_destroy(B200Encoder* e);
+int b200_encoder_device(const B200Encoder* e); /* CUDA ordinal the encoder lives on */
+/* bit d set: device d compressed at least one shard of the last BrotliEncoderCompressMulti / CompressWorkPool call (diagnostic) */
+uint32_t b200_last_multi_device_mask(void);
 int b200_encoder_set_option(B200Encoder* e, int option, uint32_t value);
 size_t b200_max_compressed_size(size_t n);
 /* device_io: 0 = in / out are host pointers; 1 = both are device pointers on the encoder's GPU; 2 = host input, device output

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -346,6 +347,9 @@ BROTLI_BOOL BrotliEncoderCompress(int quality, int lgwin, BrotliEncoderMode mode
 }
 
 // ---- multi ----
+static std::atomic<uint32_t> g_last_multi_mask{0};  // bit d set: device d compressed at least one shard of the last multi call
+uint32_t b200_last_multi_device_mask(void) { return g_last_multi_mask.load(); }
+
 static int32_t compress_multi_impl(const std::vector<B200Encoder*>& encs, const std::vector<std::mutex*>& mus, size_t num_params,
                                    const BrotliEncoderParameter* keys, const uint32_t* values, size_t input_size,
                                    const uint8_t* input, size_t* encoded_size, uint8_t* encoded, size_t desired_num_threads) {
@@ -364,8 +368,10 @@ static int32_t compress_multi_impl(const std::vector<B200Encoder*>& encs, const 
   std::vector<std::vector<uint8_t>> outs(shards);
   std::vector<int> oks(shards, 0);
   const size_t ngpu = encs.size();
+  g_last_multi_mask.store(0);
   auto work = [&](size_t g) {  // one host thread per GPU walks its shards in order
     DeviceGuard dg;
+    if (g < shards) g_last_multi_mask.fetch_or(1u << (b200_encoder_device(encs[g]) & 31));
     for (size_t i = g; i < shards; i += ngpu) {
       size_t a = i * input_size / shards, b = (i + 1) * input_size / shards;  // get_range threading/mod.rs:333
       size_t cap = b200_max_compressed_size(b - a) + 16 * ((b - a) / kSpanPiece + 1), got = 0;

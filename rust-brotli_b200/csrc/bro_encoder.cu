@@ -556,7 +556,9 @@ struct B200Encoder {
       if (hq_thread_units) k_zopfli<<<(W.num_units + 31) / 32, 32, 0, stream>>>(W, za, 1u);
       else k_zopfli<<<W.num_units, 32, 0, stream>>>(W, za, 32u);
     } else
-    if (pair_parse == 4 && P.n_last == 4 && P.hash_type != 9)  // four units per warp (q5, q6)
+    if (pair_parse == 32 && P.n_last == 4 && P.hash_type != 9)  // one unit per thread (q5, q6)
+      k_parse_thread<<<(W.num_units + PARSE_THREAD_BLOCK - 1) / PARSE_THREAD_BLOCK, PARSE_THREAD_BLOCK, 0, stream>>>(W);
+    else if (pair_parse == 4 && P.n_last == 4 && P.hash_type != 9)  // four units per warp (q5, q6)
       k_parse_pair<4><<<(W.num_units + 4 * PARSE_WARPS - 1) / (4 * PARSE_WARPS), PARSE_WARPS * 32, 0, stream>>>(W);
     else if (pair_parse && P.n_last == 4 && P.hash_type != 9)  // two units per warp
       k_parse_pair<2><<<(W.num_units + 2 * PARSE_WARPS - 1) / (2 * PARSE_WARPS), PARSE_WARPS * 32, 0, stream>>>(W);
@@ -640,6 +642,7 @@ B200Encoder* b200_encoder_create(int device) {
   }
   return e;
 }
+int b200_encoder_device(const B200Encoder* e) { return e ? e->device : -1; }
 void b200_encoder_destroy(B200Encoder* e) {
   if (!e) return;
   e->destroy();

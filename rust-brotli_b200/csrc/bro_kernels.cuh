@@ -1331,6 +1331,170 @@ __global__ void __launch_bounds__(PARSE_WARPS * 32, 10) k_parse_pair(Workspace W
   }
 }
 
+// One parse unit per THREAD (q5 / q6).  The lane-parallel kernels above spend most of their issue slots keeping 8..32 lanes in
+// step around a walk that is sequential by nature; here every thread simply runs parse_range() for its own unit, written as a
+// three-phase state machine so that the 32 units of a warp never wait for each other's rare long paths:
+//   PROBE   one position q (pos, or pos + 1 while a match is pending): first 8 bytes of the 4 cached distances and the bucket
+//           candidate of best[q]; candidates that are not finished by those 8 bytes (or that were capped by the match stage) are
+//           flagged,
+//   EXTEND  one flagged candidate grows by up to 8 bytes per turn (other threads meanwhile go on with their own phases),
+//   DECIDE  the fold of find_match() (highest score, lowest cache index on ties; the bucket candidate must be strictly better)
+//           and the greedy / lazy step of parse_range().
+// A warp retires 32 probes per ~200 instructions instead of 2..8; what it pays is memory divergence (every load touches 32
+// lines), which is why loads are few and wide.
+__device__ __forceinline__ uint64_t ld8_unaligned(const uint8_t* p) {  // 2 aligned 8-byte loads instead of 3 4-byte loads
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint2* q = reinterpret_cast<const uint2*>(a & ~(uintptr_t)7);
+  const uint2 v0 = __ldg(q), v1 = __ldg(q + 1);
+  const bool up = (a & 4u) != 0;
+  const uint32_t w0 = up ? v0.y : v0.x, w1 = up ? v1.x : v0.y, w2 = up ? v1.y : v1.x;
+  const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+  return ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
+}
+
+#ifndef PARSE_THREAD_BLOCK
+#define PARSE_THREAD_BLOCK 32
+#endif
+__global__ void __launch_bounds__(PARSE_THREAD_BLOCK) k_parse_thread(Workspace W) {
+  const uint32_t u = blockIdx.x * PARSE_THREAD_BLOCK + threadIdx.x;
+  if (u >= W.num_units) return;
+  const EncParams& P = W.P;
+  const uint8_t* __restrict__ data = W.data;
+  const uint32_t* __restrict__ best = W.best;
+  const uint32_t s = u * P.unit, e = bmin(P.n, s + P.unit);
+  uint32_t* const out_w = reinterpret_cast<uint32_t*>(W.raw + (size_t)u * (P.unit / 2 + 1));
+  const uint32_t htl = P.hash_type == 6 ? 8u : 4u;
+  const uint32_t window = 64u;
+  const bool D = P.use_dict != 0;
+  const bool near_start = P.abs_base < P.max_backward;
+  const uint32_t lcap = P.lcap;
+  const bool warm = (u % P.mb_units) != 0 && s >= BRO_WARMUP_BYTES;
+  int stage = warm ? 0 : 1;  // 0 warm-up in front of the unit, 1 the unit, 2 done
+  uint32_t pos = stage == 0 ? s - BRO_WARMUP_BYTES : s, uend = stage == 0 ? s : e;
+  uint32_t insert_len = 0, ncmd = 0, copied = 0, arh = pos + window;
+  bool have_m = false;
+  uint32_t m_len = 0, m_dist = 0, m_score = 0;
+  int delayed = 0;
+  int32_t dc0 = 0x3fffffff, dc1 = 0x3fffffff, dc2 = 0x3fffffff, dc3 = 0x3fffffff;
+  uint32_t tail_out = 0, ncopy_out = 0, ncmd_out = 0;
+  auto advance = [&]() {
+    if (stage < 2 && !(have_m || pos + htl < uend)) {
+      if (stage == 1) { tail_out = insert_len + (uend - pos); ncopy_out = copied; ncmd_out = ncmd; stage = 2; }
+      else { stage = 1; pos = s; uend = e; insert_len = 0; ncmd = 0; copied = 0; arh = s + window; }
+    }
+  };
+  advance();
+  advance();
+  enum { PROBE = 0, EXTEND = 1, DECIDE = 2 };
+  int phase = PROBE;
+  uint32_t q = 0, maxl = 0, mb = 0, ext = 0, b = 0, bdist = 0;
+  uint32_t l0 = 0, l1 = 0, l2 = 0, l3 = 0, l4 = 0;
+  while (stage < 2) {
+    if (phase == PROBE) {
+      q = pos + (have_m ? 1u : 0u);
+      maxl = uend - q;
+      mb = near_start ? bmin(q + P.abs_base, P.max_backward) : P.max_backward;
+      const uint64_t c = ld8_unaligned(data + q);
+      b = __ldg(best + q);
+      ext = 0;
+      const uint32_t cap8 = bmin(8u, maxl);
+      auto probe = [&](int32_t back, uint32_t bit) -> uint32_t {
+        const bool ok = back > 0 && (uint32_t)back <= mb;
+        const uint64_t x = c ^ ld8_unaligned(data + q - (ok ? (uint32_t)back : 0u));
+        uint32_t l = x ? ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : 8u;
+        l = bmin(l, cap8);
+        if (ok && l == 8u && maxl > 8u) ext |= bit;
+        return ok ? l : 0u;
+      };
+      l0 = probe(dc0, 1u);
+      l1 = probe(dc1, 2u);
+      l2 = probe(dc2, 4u);
+      l3 = probe(dc3, 8u);
+      l4 = 0;
+      bdist = b >> 8;
+      if (!(b & BRO_BEST_DICT) && (b & 0xFFu) != 0) {
+        const uint32_t blen = b & 0xFFu;
+        l4 = bmin(blen, maxl);
+        if (blen >= lcap && maxl > l4) ext |= 16u;
+      }
+      phase = ext ? EXTEND : DECIDE;
+    }
+    if (phase == EXTEND) {
+      const uint32_t k = (uint32_t)__ffs((int)ext) - 1u;
+      const uint32_t back = k == 0 ? (uint32_t)dc0 : (k == 1 ? (uint32_t)dc1 : (k == 2 ? (uint32_t)dc2 : (k == 3 ? (uint32_t)dc3 : bdist)));
+      uint32_t l = k == 0 ? l0 : (k == 1 ? l1 : (k == 2 ? l2 : (k == 3 ? l3 : l4)));
+      const uint8_t* pa = data + q + l;
+      const uint64_t x = ld8_unaligned(pa) ^ ld8_unaligned(pa - back);
+      const uint32_t mism = x ? ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : 8u;
+      l += bmin(mism, maxl - l);
+      if (mism < 8u || l >= maxl) ext &= ext - 1u;
+      if (k == 0) l0 = l; else if (k == 1) l1 = l; else if (k == 2) l2 = l; else if (k == 3) l3 = l; else l4 = l;
+      if (!ext) phase = DECIDE;
+    }
+    if (phase == DECIDE) {
+      phase = PROBE;
+      uint32_t key = 0;
+      if (l0 >= 2u) key = (score_last_distance(5, l0, 0) << 2) | 3u;
+      if (l1 >= 2u) key = max(key, (score_last_distance(5, l1, 1) << 2) | 2u);
+      if (l2 >= 3u) key = max(key, (score_last_distance(5, l2, 2) << 2) | 1u);
+      if (l3 >= 3u) key = max(key, (score_last_distance(5, l3, 3) << 2) | 0u);
+      bool f_found = key != 0;
+      const uint32_t wi = 3u - (key & 3u);
+      uint32_t f_len = f_found ? (wi == 0 ? l0 : (wi == 1 ? l1 : (wi == 2 ? l2 : l3))) : 0u;
+      uint32_t f_dist = f_found ? (uint32_t)(wi == 0 ? dc0 : (wi == 1 ? dc1 : (wi == 2 ? dc2 : dc3))) : 0u;
+      uint32_t f_score = f_found ? (key >> 2) : BRO_MIN_SCORE;
+      if (b & BRO_BEST_DICT) {
+        Match dm;
+        if (!f_found && D && dict_decode(b, 5, maxl, mb, &dm)) { f_found = true; f_len = dm.len; f_dist = dm.dist; f_score = dm.score; }
+      } else if (l4 >= 4u) {
+        const uint32_t score = score_regular(5, l4, bdist);
+        if (f_score < score) { f_score = score; f_len = l4; f_dist = bdist; f_found = true; }
+      }
+      bool accept = false;
+      if (!have_m) {
+        if (f_found) {
+          m_len = f_len; m_dist = f_dist; m_score = f_score;
+          have_m = true;
+          delayed = 0;
+        } else {
+          insert_len++;
+          pos++;
+          if (pos > arh) {
+            const uint32_t margin = bmax(htl - 1u, 4u);
+            if (pos + 16 + margin >= uend) { insert_len += uend - pos; pos = uend; }
+            else if (pos > arh + 4 * window) { insert_len += 16; pos += 16; }
+            else { insert_len += 8; pos += 8; }
+          }
+        }
+      } else {
+        accept = true;
+        if (f_found && f_score >= m_score + 175u) {
+          pos++;
+          insert_len++;
+          m_len = f_len; m_dist = f_dist; m_score = f_score;
+          if (++delayed < 4 && pos + htl < uend) accept = false;
+        }
+      }
+      if (accept) {
+        const uint32_t m_bytes = len_bytes(m_len);
+        arh = pos + 2 * m_bytes + window;
+        if (!len_is_dict(m_len) && (int32_t)m_dist != dc0) { dc3 = dc2; dc2 = dc1; dc1 = dc0; dc0 = (int32_t)m_dist; }
+        if (stage == 1) { out_w[3u * ncmd] = insert_len; out_w[3u * ncmd + 1u] = m_len; out_w[3u * ncmd + 2u] = m_dist; }
+        ++ncmd;
+        insert_len = 0;
+        copied += m_bytes;
+        pos += m_bytes;
+        have_m = false;
+      }
+      advance();
+      advance();
+    }
+  }
+  W.unit_ncmd[u] = ncmd_out;
+  W.unit_tail[u] = tail_out;
+  W.unit_ncopy[u] = ncopy_out;
+}
+
 #ifndef PARSE_MIN_BLOCKS
 #define PARSE_MIN_BLOCKS 10
 #endif

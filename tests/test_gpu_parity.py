@@ -321,6 +321,33 @@ def test_config4_json_q9_one_shard_512mib():
     assert hashlib.sha256(sys_decompress(c, len(d))).digest() == hashlib.sha256(d).digest()
 
 
+def test_compress_multi_across_physical_gpus(encoder):
+    """BrotliEncoderCompressMulti (src/ffi/multicompress/mod.rs:93; compress_multi threading/mod.rs:413) with 8 shards on a box
+    with more than one GPU: one host thread per GPU, shards round-robin over the devices.  The stream must be the one a single
+    GPU produces shard by shard (the kernels are deterministic), must decode, and more than one device must have worked."""
+    import ctypes
+    import rust_brotli_b200 as rb
+    from tools import datagen
+    L = rb.lib()
+    L.b200_device_count.restype = ctypes.c_int
+    ngpu = L.b200_device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 visible GPUs (run under gpurun --gpus 2)")
+    d = datagen.json_logs(64_000_000) * 2
+    c = rb.compress_multi(rb.BrotliEncoderParams(quality=9, lgwin=22), d, 8)
+    L.b200_last_multi_device_mask.restype = ctypes.c_uint32
+    mask = L.b200_last_multi_device_mask()
+    assert bin(mask).count("1") == min(ngpu, 8), "shards ran on devices %s of %d" % (bin(mask), ngpu)
+    assert hashlib.sha256(sys_decompress(c, len(d))).digest() == hashlib.sha256(d).digest()
+    parts = []
+    for i in range(8):
+        a, b = i * len(d) // 8, (i + 1) * len(d) // 8
+        win = (1 << 22) + 65536  # csrc/bro_capi.cu compress_span: the prefix handed over is re-based to one window (+ slack) in front
+        lo = ((a - win) & ~4095) if a > win else 0
+        parts.append(encoder.compress_range(d[lo:b], a - lo, b - a, 9, 22, i == 0, i == 7, True, size_hint=b - a))
+    assert b"".join(parts) == c
+
+
 def test_config5_quickfox_tiled_512mib_q11_lgwin24(encoder):
     """configs[4]: quickfox_repeated tiled to 512 MiB, quality 11 (all-matches + shortest-path parse + BrotliSplitBlock +
     clustered context maps on the device), lgwin 24.  libbrotlienc q11 needs 58 B for 16 MB of this input (one copy per
