@@ -78,8 +78,11 @@ typedef struct BrotliEncoderWorkPoolStruct BrotliEncoderWorkPool;
 /* :72  BrotliEncoderCreateInstance.  Host-side bookkeeping uses alloc_func when given; device memory is owned by the state. */
 BrotliEncoderState* BrotliEncoderCreateInstance(brotli_alloc_func alloc_func, brotli_free_func free_func, void* opaque);
 /* :115 BrotliEncoderSetParameter (refused after the first byte was consumed, encode.rs:289-295).  Also refused
- * (BROTLI_FALSE, state unchanged): a value this path cannot honour -- LARGE_WINDOW != 0 and the framing parameters
- * (CATABLE, APPENDABLE, MAGIC_NUMBER, BYTE_ALIGN, BARE_STREAM) unless INTEGRATION.md lists the mode as produced.
+ * (BROTLI_FALSE, state unchanged): a value this path cannot honour -- LARGE_WINDOW != 0, LGBLOCK outside 0 / 16..24.
+ * Framing parameters act as in the reference (encode.rs:264-283, :559-568, :1928-1940, :2258-2333): CATABLE (first two bytes as an
+ * uncompressed metablock, no static dictionary, implies APPENDABLE), APPENDABLE, MAGIC_NUMBER (metadata metablock e1 97 8x,
+ * VERSION, size hint), BYTE_ALIGN (padding metablock in front of the final empty one), BARE_STREAM (no final metablock; with
+ * CATABLE no window bits either).  Streams made with CATABLE go through the reference's BroCatli (src/concat/mod.rs).
  * QUALITY: 5..9 run the hash-chain family, 10 and 11 the optimal-parse family; values below 5 run as 5 (the q0..q4
  * hashers are not built) -- b200_effective_quality() reports the quality that will really be used. */
 BROTLI_BOOL BrotliEncoderSetParameter(BrotliEncoderState* state, BrotliEncoderParameter p, uint32_t value);

@@ -28,10 +28,14 @@ struct EncoderParams {  // the subset of BrotliEncoderParams (backward_reference
   int catable = 0, appendable = 0, magic_number = 0, byte_align = 0, bare_stream = 0;
 };
 
-// Framing modes the device path can produce today.  Everything else makes SetParameter / CompressMulti fail.
-bool framing_supported(const EncoderParams& p) {
-  return !p.catable && !p.appendable && !p.magic_number && !p.byte_align && !p.bare_stream;
+// Stream framing (encode.rs:559-568 SanitizeParams): catable implies appendable and no static dictionary; a bare stream is byte
+// aligned; byte alignment only means something for appendable / bare streams.
+void sanitize_framing(EncoderParams& p) {
+  if (p.catable) { p.appendable = 1; p.no_dictionary = 1; }
+  if (p.bare_stream) p.byte_align = 1;
+  else if (!p.appendable) p.byte_align = 0;
 }
+bool framed(const EncoderParams& p) { return p.catable || p.appendable || p.magic_number || p.byte_align || p.bare_stream; }
 
 // Applies one parameter; a value this path cannot honour leaves `p` unchanged and returns false (the reference's
 // set_parameter returns false only after initialisation, encode.rs:289-295 -- here "accepted" also means "will act").
@@ -48,17 +52,16 @@ bool apply_param(EncoderParams& p, int key, uint32_t value) {
     case BROTLI_PARAM_SIZE_HINT: q.size_hint = value; break;
     case BROTLI_PARAM_NO_DICTIONARY: q.no_dictionary = value != 0; break;
     case BROTLI_PARAM_LARGE_WINDOW: if (value != 0) return false; break;  // windows above 2^24 are not produced
-    // stream framing (encode.rs:2283-2333, :1972-1975)
-    case BROTLI_PARAM_CATABLE: q.catable = value != 0; if (q.catable) q.appendable = 1; break;
+    // stream framing (encode.rs:264-283; acted on by compress_framed below)
+    case BROTLI_PARAM_CATABLE: q.catable = value != 0; if (!q.appendable) q.appendable = value != 0; break;
     case BROTLI_PARAM_APPENDABLE: q.appendable = value != 0; break;
     case BROTLI_PARAM_MAGIC_NUMBER: q.magic_number = value != 0; break;
     case BROTLI_PARAM_BYTE_ALIGN: q.byte_align = value != 0; break;
-    case BROTLI_PARAM_BARE_STREAM: q.bare_stream = value != 0; if (q.bare_stream) q.byte_align = 1; break;
+    case BROTLI_PARAM_BARE_STREAM: q.bare_stream = value != 0; if (!q.byte_align) q.byte_align = value != 0; break;
     default:
       // research / divans knobs of the reference (stride, prior, cdf speeds ...) have no effect on this path
       if (!(key >= 150 && key <= 173)) return false;
   }
-  if (!framing_supported(q)) return false;
   p = q;
   return true;
 }
@@ -148,6 +151,91 @@ static bool compress_span(B200Encoder* enc, const EncoderParams& p, uint64_t hin
   return true;
 }
 
+// ---- stream framing around compress_span (catable / appendable / magic_number / byte_align / bare_stream) ----
+struct HostBits {  // LSB-first bit writer into a bounded host buffer
+  uint8_t* out; size_t cap; uint64_t pos = 0; bool ok = true;
+  void put(uint32_t nbits, uint64_t v) {
+    for (uint32_t i = 0; i < nbits; ++i, ++pos) {
+      if ((pos >> 3) >= cap) { ok = false; return; }
+      if ((pos & 7) == 0) out[pos >> 3] = 0;
+      out[pos >> 3] |= (uint8_t)(((v >> i) & 1u) << (pos & 7));
+    }
+  }
+  void align() { while (ok && (pos & 7)) put(1, 0); }
+  void bytes(const uint8_t* p, size_t n) { for (size_t i = 0; i < n; ++i) put(8, p[i]); }
+};
+static void put_window_bits(HostBits& w, int lgwin) {  // EncodeWindowBits encode.rs:600-627 (no large window)
+  if (lgwin == 16) w.put(1, 0);
+  else if (lgwin == 17) w.put(7, 1);
+  else if (lgwin > 17) w.put(4, (uint64_t)(((lgwin - 17) << 1) | 1));
+  else w.put(7, (uint64_t)(((lgwin - 8) << 4) | 1));
+}
+// Compresses input[a, b) like compress_span and wraps it in the framing `p` asks for:
+//   first: [window bits unless catable && bare] [magic-number metadata metablock, brotli_bit_stream.rs:2869-2896]
+//          [catable: the first min(2, len) bytes as an uncompressed metablock, encode.rs:2285-2333 -- a stitched stream's literal
+//          contexts then never look into the previous file]
+//   last:  [byte_align: padding metablock][unless bare: the empty last metablock]  (WriteEmptyLastBlocksInternal encode.rs:1928-1940)
+// Data metablocks never carry ISLAST on this path, so "appendable" (encode.rs:1973-1975) needs nothing more, and every
+// metablock starts with an unknown distance cache, which is what catable's 0x7ffffff0 cache (encode.rs:693-703) asks for.
+static bool compress_framed(B200Encoder* enc, EncoderParams p, uint64_t hint, const uint8_t* input, size_t a, size_t b, bool first,
+                            bool last, bool align_end, uint8_t* out, size_t out_cap, size_t* out_size) {
+  sanitize_framing(p);
+  if (!framed(p)) return compress_span(enc, p, hint, input, a, b, first, last, align_end, out, out_cap, out_size);
+  const int lw = p.lgwin < 10 ? 10 : (p.lgwin > 24 ? 24 : p.lgwin);
+  HostBits w{out, out_cap};
+  size_t body_a = a;
+  bool dev_first = first;
+  if (first && (p.magic_number || p.catable || a == b)) {
+    dev_first = false;
+    if (!(p.catable && p.bare_stream)) put_window_bits(w, lw);
+    if (p.magic_number) {
+      uint8_t sh[10]; size_t nsh = 0;
+      for (uint64_t v = p.size_hint;;) {  // encode_base_128 brotli_bit_stream.rs:2855-2867
+        sh[nsh] = (uint8_t)(v & 0x7f); v >>= 7;
+        if (v) sh[nsh++] |= 0x80; else { ++nsh; break; }
+        if (nsh == 10) break;
+      }
+      w.put(1, 0); w.put(2, 3); w.put(1, 0); w.put(2, 1); w.put(8, 3 + nsh);
+      w.align();
+      const uint8_t magic[4] = {0xe1, 0x97, (uint8_t)(p.catable ? 0x81 : (p.appendable ? 0x82 : 0x80)), 1 /* crate VERSION, lib.rs:67 */};
+      w.bytes(magic, 4);
+      w.bytes(sh, nsh);
+    }
+    if (p.catable && b > a) {
+      const size_t n2 = std::min<size_t>(2, b - a);
+      w.put(1, 0); w.put(2, 0); w.put(16, n2 - 1); w.put(1, 1);  // ISLAST 0, MNIBBLES 4, MLEN - 1, ISUNCOMPRESSED
+      w.align();
+      w.bytes(input + a, n2);
+      body_a += n2;
+    }
+  }
+  if (!w.ok) return false;
+  size_t off = (size_t)(w.pos >> 3);
+  if (body_a < b) {
+    if (w.pos & 7) return false;  // cannot happen: a prologue in front of data ends with a byte-aligned metablock
+    // the device writes the plain 2-bit trailer itself when no alignment is asked for
+    const bool dev_last = last && !p.byte_align && !p.bare_stream;
+    const bool dev_align = last ? (p.byte_align != 0) : align_end;
+    size_t got = 0;
+    if (!compress_span(enc, p, hint, input, body_a, b, dev_first, dev_last, dev_align, out + off, out_cap - off, &got)) return false;
+    off += got;
+    if (last && p.byte_align && !p.bare_stream) {
+      if (off >= out_cap) return false;
+      out[off++] = 3;  // ISLAST + ISLASTEMPTY on a byte boundary
+    }
+    *out_size = off;
+    return true;
+  }
+  // nothing (left) to compress: the trailer follows the prologue directly
+  if (last) {
+    if (p.byte_align && (w.pos & 7)) { w.put(6, 6); w.align(); }  // BrotliWritePaddingMetaBlock
+    if (!p.bare_stream) { w.put(2, 3); w.align(); }
+  } else if (align_end && (w.pos & 7)) { w.put(6, 6); w.align(); }
+  if (!w.ok || (w.pos & 7)) return false;
+  *out_size = (size_t)(w.pos >> 3);
+  return true;
+}
+
 extern "C" {
 
 uint32_t BrotliEncoderVersion(void) { return 0x08000004u; /* tracks crate 8.0.4 */ }
@@ -230,22 +318,24 @@ void BrotliEncoderFreeUsize(BrotliEncoderState* s, size_t* data, size_t size) { 
 static bool state_emit(BrotliEncoderStateStruct* s, bool last, uint64_t upto) {
   const uint64_t start = s->flushed, len = upto - start;
   const bool first = !s->header_written;
-  if (len == 0) {
+  EncoderParams fp = s->params;
+  sanitize_framing(fp);
+  if (len == 0 && !(framed(fp) && first)) {
     if (last) {
       if (first) s->output.push_back(6);        // empty stream, encode.rs:1463
-      else s->output.push_back(3);              // ISLAST + ISLASTEMPTY after a byte-aligned flush
+      else if (!fp.bare_stream) s->output.push_back(3);  // ISLAST + ISLASTEMPTY after a byte-aligned flush
       s->header_written = true;
     }
     return true;
   }
-  size_t cap = b200_max_compressed_size(len) + 16, got = 0;
+  size_t cap = b200_max_compressed_size(len) + 64, got = 0;
   size_t old = s->output.size();
   s->output.resize(old + cap);
   uint64_t hint = s->params.size_hint ? s->params.size_hint : s->base + s->input.size() - s->dict_len;
   // positions are relative to `base`: once a prefix has been dropped at least a full window precedes `start`, so the
   // window limit min(position, 2^lgwin - 16) is the same in both coordinate systems
-  bool ok = compress_span(s->enc, s->params, hint, s->input.data(), (size_t)(start - s->base), (size_t)(upto - s->base), first, last,
-                          true, s->output.data() + old, cap, &got);
+  bool ok = compress_framed(s->enc, s->params, hint, s->input.data(), (size_t)(start - s->base), (size_t)(upto - s->base), first, last,
+                            true, s->output.data() + old, cap, &got);
   if (!ok) { s->output.resize(old); return false; }
   s->output.resize(old + got);
   s->flushed = upto;
@@ -359,6 +449,16 @@ static int32_t compress_multi_impl(const std::vector<B200Encoder*>& encs, const 
     if (!apply_param(p, (int)keys[i], values[i])) return 0;  // a parameter this path cannot honour fails the call
   size_t shards = std::min<size_t>(desired_num_threads, 16);  // MAX_THREADS, fixed_queue.rs:1
   if (input_size == 0) {
+    EncoderParams fp = p;
+    sanitize_framing(fp);
+    if (framed(fp)) {  // header / magic number / trailer of an empty framed stream
+      uint8_t tmp[64];
+      size_t got = 0;
+      if (!compress_framed(encs[0], p, 0, input, 0, 0, true, true, false, tmp, sizeof(tmp), &got) || got > *encoded_size) return 0;
+      memcpy(encoded, tmp, got);
+      *encoded_size = got;
+      return 1;
+    }
     if (*encoded_size < 1) return 0;
     encoded[0] = 6;
     *encoded_size = 1;
@@ -374,12 +474,12 @@ static int32_t compress_multi_impl(const std::vector<B200Encoder*>& encs, const 
     if (g < shards) g_last_multi_mask.fetch_or(1u << (b200_encoder_device(encs[g]) & 31));
     for (size_t i = g; i < shards; i += ngpu) {
       size_t a = i * input_size / shards, b = (i + 1) * input_size / shards;  // get_range threading/mod.rs:333
-      size_t cap = b200_max_compressed_size(b - a) + 16 * ((b - a) / kSpanPiece + 1), got = 0;
+      size_t cap = b200_max_compressed_size(b - a) + 16 * ((b - a) / kSpanPiece + 1) + 64, got = 0;
       outs[i].resize(cap);
       std::lock_guard<std::mutex> lk(*mus[g]);
       // compress_part threading/mod.rs:337-383: size_hint = shard length
       uint64_t hint = p.size_hint ? p.size_hint : (b - a);
-      oks[i] = compress_span(encs[g], p, hint, input, a, b, i == 0, i + 1 == shards, true, outs[i].data(), cap, &got) ? 1 : 0;
+      oks[i] = compress_framed(encs[g], p, hint, input, a, b, i == 0, i + 1 == shards, true, outs[i].data(), cap, &got) ? 1 : 0;
       outs[i].resize(oks[i] ? got : 0);
     }
   };

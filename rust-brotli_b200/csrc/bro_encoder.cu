@@ -115,6 +115,7 @@ struct B200Encoder {
   uint32_t hq_unit = 16384;  // parse unit of the shortest-path parse (quality >= 10)
   int hq_thread_units = 0;   // 1: one parse unit per thread instead of one per warp (A/B switch)
   int num_lanes = 4;
+  int ondemand = 1;       // q7..q9: search deep buckets where the parse stands (1) or for every position up front (0, A/B)
   int pair_parse = 4;     // parse units per warp for q5 / q6: 4 (default) or 2; 0 = one unit per warp (kept for A/B measurements)
   int shallow_match = 1;  // branch-free candidate scan for depth 16 / 32 (0: loop version, kept for A/B measurements)
   Lane lanes[kMaxLanes];
@@ -478,6 +479,11 @@ struct B200Encoder {
     // ---- sort + match, batch by batch ----
     const uint32_t window = 1u << P.lgwin;
     const uint32_t payload_max = kBatchMax - window - 4096;
+    // q7..q9 (bucket depth >= 64): the parse searches the buckets on demand when the chunk is a single sort batch
+    const bool od = ondemand && P.quality < 10 && (P.depth == 64 || P.depth == 128 || P.depth == 256) && range_len <= payload_max &&
+                    (P.n_last == 4 || P.n_last == 10 || P.n_last == 16) && (ondemand > 1 || range_len >= ((uint32_t)4 << 20));
+    DeepArgs da;
+    memset(&da, 0, sizeof(da));
     for (uint64_t b0 = range_start; b0 < (uint64_t)range_start + range_len; b0 += payload_max) {
       const uint32_t b1 = (uint32_t)std::min<uint64_t>((uint64_t)range_start + range_len, b0 + payload_max);
       uint32_t origin = b0 > window ? (uint32_t)b0 - window : 0u;
@@ -522,6 +528,11 @@ struct B200Encoder {
       const size_t smem = (size_t)(MATCH_THREADS + P.depth) * 6 * 4;
       mark(L, B200_ST_MATCH);
       const uint32_t mgrid = (count + MATCH_THREADS - 1) / MATCH_THREADS;
+      if (od) {  // ranks into best[], signatures into the free half of the sort ping-pong
+        da.m = ma;
+        da.sig = L.d_sortA.as<uint32_t>();
+        k_rank_sig<<<(count + 255) / 256, 256, 0, stream>>>(ma, L.d_sortA.as<uint32_t>());
+      } else
       if (P.quality >= 10) {  // all matches of every position
         MatchAllArgs aa;
         aa.m = ma;
@@ -555,6 +566,19 @@ struct B200Encoder {
       za.scratch = L.d_hq_scratch.as<uint32_t>();
       if (hq_thread_units) k_zopfli<<<(W.num_units + 31) / 32, 32, 0, stream>>>(W, za, 1u);
       else k_zopfli<<<W.num_units, 32, 0, stream>>>(W, za, 32u);
+    } else
+    if (od) {
+      const uint32_t pg = (W.num_units + PARSE_WARPS - 1) / PARSE_WARPS;
+#define B200_OD_LAUNCH(NLV) \
+      switch (P.depth) { \
+        case 64: k_parse_ondemand<NLV, 64><<<pg, PARSE_WARPS * 32, 0, stream>>>(W, da); break; \
+        case 128: k_parse_ondemand<NLV, 128><<<pg, PARSE_WARPS * 32, 0, stream>>>(W, da); break; \
+        default: k_parse_ondemand<NLV, 256><<<pg, PARSE_WARPS * 32, 0, stream>>>(W, da); break; \
+      }
+      if (P.n_last == 4) { B200_OD_LAUNCH(4) }
+      else if (P.n_last == 10) { B200_OD_LAUNCH(10) }
+      else { B200_OD_LAUNCH(16) }
+#undef B200_OD_LAUNCH
     } else
     if (pair_parse == 32 && P.n_last == 4 && P.hash_type != 9)  // one unit per thread (q5, q6)
       k_parse_thread<<<(W.num_units + PARSE_THREAD_BLOCK - 1) / PARSE_THREAD_BLOCK, PARSE_THREAD_BLOCK, 0, stream>>>(W);
@@ -661,6 +685,7 @@ int b200_encoder_set_option(B200Encoder* e, int option, uint32_t value) {
     case B200_OPT_DICT: e->use_dict = (int)value; return 1;
     case B200_OPT_SHALLOW_MATCH: e->shallow_match = (int)value; return 1;
     case B200_OPT_PAIR_PARSE: e->pair_parse = (int)value; return 1;
+    case B200_OPT_ONDEMAND: e->ondemand = (int)value; return 1;
     case B200_OPT_HQ_SPLIT: e->hq_split = (int)value; return 1;
     case B200_OPT_HQ_UNIT: e->hq_unit = value; return 1;
     case B200_OPT_HQ_THREAD_UNITS: e->hq_thread_units = (int)value; return 1;

@@ -1495,6 +1495,266 @@ __global__ void __launch_bounds__(PARSE_THREAD_BLOCK) k_parse_thread(Workspace W
   W.unit_ncopy[u] = ncopy_out;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Deep buckets, searched on demand (q7..q9).  k_match_deep looks at up to 256 candidates for EVERY position, but the greedy / lazy
+// walk only ever asks for the positions it visits -- about half of them on text, a tenth on record-structured data with long
+// copies.  The reference has the same shape (FindLongestMatch runs where the parse stands, mod.rs:2376-2552); what it cannot do is
+// run 6144 walks at once.  Here one warp walks one unit exactly like parse_range(), and at every position it stands on the 32 lanes
+// search the bucket list of the sort stage: rank[p] (written by k_rank_sig into the best[] buffer) is the position's index in the
+// sorted list, the `depth` entries in front of it are its candidates, nearest first, 32 per round.  sig[] carries, in sorted order,
+// key << 17 | 17 hash bits of the entry's first four bytes, so bucket end and the four-byte filter are decided from two coalesced
+// 128-byte reads; only the surviving candidates touch their data.  The value computed for a position is exactly k_match_deep's
+// best[p], so the walk below is parse_range() / find_match() of bro_parse.cuh and the streams are identical.
+// ---------------------------------------------------------------------------------------------------
+struct DeepArgs {
+  MatchArgs m;          // sorted list of the chunk's (single) batch; m.best holds the ranks
+  const uint32_t* sig;  // [m.count]
+};
+__device__ __forceinline__ uint32_t entry_sig(int hash_type, int key_bits, uint32_t w0, uint32_t w1) {
+  return (hash_key_from_words(hash_type, key_bits, w0, w1) << 17) | ((w0 * 0x9E3779B1u) >> 15);
+}
+__global__ void __launch_bounds__(256) k_rank_sig(MatchArgs a, uint32_t* sig) {
+  const uint32_t j = blockIdx.x * 256u + threadIdx.x;
+  if (j >= a.count) return;
+  const uint32_t pos = a.sorted[j];
+  const uint64_t w = ldu64(a.data + a.origin + pos);
+  sig[j] = entry_sig(a.hash_type, a.key_bits, (uint32_t)w, (uint32_t)(w >> 32));
+  if (pos >= a.payload_begin) a.best[a.origin + pos] = j;
+}
+
+// best[p] of k_match_deep for the absolute position p, computed by the whole warp (result uniform).  r = rank of p in the sorted
+// list, s_back = 256 words of shared memory owned by this warp.  A walk is a chain of dependent positions, so what counts is the
+// number of memory round trips per position:
+//   1. positions and signatures of all DEPTH candidates in one go (lane l: candidates l, l + 32, ..; coalesced), bucket / window
+//      end by ballots; the distances of the candidates whose signature agrees are compacted into s_back, nearest first,
+//   2. those survivors 32 at a time: first 8 bytes, then 8 more per trip; a candidate that cannot be strictly longer than the
+//      best so far is dropped after one byte, and a full-length match ends the search (both exact: a farther candidate that is
+//      not longer cannot score higher, score_regular is monotone in both).
+template <int DEPTH>
+__device__ __forceinline__ uint32_t deep_best_warp(const DeepArgs& A, uint32_t p, uint32_t r, uint32_t* s_back) {
+  constexpr int T = DEPTH / 32;
+  const MatchArgs& a = A.m;
+  const uint32_t FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x & 31;
+  if (a.n - p < 8) return 0u;
+  const uint32_t prel = p - a.origin;
+  const uint8_t* cur = a.data + p;
+  const uint64_t c8 = ldu64(cur);
+  const uint32_t mysig = entry_sig(a.hash_type, a.key_bits, (uint32_t)c8, (uint32_t)(c8 >> 32));
+  const uint32_t maxl = bmin(a.lcap, a.n - p);
+  const uint32_t mbk = bmin(p, a.max_backward);
+  const uint32_t kNone = (BRO_MIN_SCORE << 16) | 0xFFFFu;
+  uint32_t cpos[T], csig[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const uint32_t k = (uint32_t)t * 32u + lane;
+    cpos[t] = 0; csig[t] = ~mysig;
+    if (r >= k + 1u) {
+      const uint32_t j = r - 1u - k;
+      cpos[t] = __ldg(a.sorted + j);
+      csig[t] = __ldg(A.sig + j);
+    }
+  }
+  uint32_t S = 0;  // survivors so far
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const uint32_t k = (uint32_t)t * 32u + lane;
+    const uint32_t backward = prel - cpos[t];
+    const bool inwin = r >= k + 1u && (csig[t] >> 17) == (mysig >> 17) && backward <= mbk;  // failing lanes form a suffix
+    const uint32_t ended = __ballot_sync(FULL, !inwin);
+    const uint32_t surv = __ballot_sync(FULL, inwin && csig[t] == mysig);
+    if (inwin && csig[t] == mysig) s_back[S + __popc(surv & ((1u << lane) - 1u))] = backward;
+    S += __popc(surv);
+    if (ended) break;
+  }
+  __syncwarp();
+  uint32_t bestk = kNone, bl = 0;
+  for (uint32_t base = 0; base < S; base += 32) {
+    const uint32_t sidx = base + lane;
+    uint32_t cand = 0;
+    if (sidx < S) {
+      const uint32_t backward = s_back[sidx];
+      const uint8_t* cp = cur - backward;
+      const uint64_t x = ldu64(cp) ^ c8;
+      if ((uint32_t)x == 0u) {  // else: signature collision
+        uint32_t len = 0;
+        if (x) len = 4u + ((uint32_t)(__ffs((int)(uint32_t)(x >> 32)) - 1) >> 3);
+        else if (!(bl >= 8u && bl < maxl && cur[bl] != cp[bl])) {
+          len = 8;
+          while (len + 8 <= maxl) {
+            const uint64_t y = ldu64(cur + len) ^ ldu64(cp + len);
+            if (y) { len += (uint32_t)(__ffsll((long long)y) - 1) >> 3; break; }
+            len += 8;
+          }
+          if (len + 8 > maxl) while (len < maxl && cur[len] == cp[len]) ++len;
+        }
+        if (len) {
+          len = bmin(len, maxl);
+          cand = (score_regular(a.hash_type, len, backward) << 16) | ((255u - sidx) << 8) | len;
+        }
+      }
+    }
+    const uint32_t wmax = __reduce_max_sync(FULL, cand);
+    if (wmax > bestk) { bestk = wmax; bl = wmax & 0xFFu; }
+    if (bestk != kNone && bl == maxl) break;
+  }
+  uint32_t res = 0;
+  if (bestk != kNone) res = (s_back[255u - ((bestk >> 8) & 0xFFu)] << 8) | (bestk & 0xFFu);
+  else if (a.use_dict) {
+    const uint64_t c16 = ldu64(cur + 8);
+    res = dict_candidate_dev(a.dict, a.hash_type, (uint32_t)c8, (uint32_t)(c8 >> 32), (uint32_t)c16, (uint32_t)(c16 >> 32), cur, a.n - p, mbk);
+  }
+  __syncwarp();
+  return res;
+}
+
+// find_match() of bro_parse.cuh at the range-relative position pos, whole warp: lane i probes cached distance i, then the bucket
+template <int NL, int DEPTH>
+__device__ __forceinline__ bool find_match_ondemand(const EncParams& P, const DeepArgs& A, const uint8_t* data, const int32_t* dca,
+                                                    uint32_t pos, uint32_t maxl, bool D, uint32_t rank, uint32_t* s_back, Match* out) {
+  constexpr uint32_t CAPA = 8;
+  const uint32_t FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x & 31;
+  const int ht = NL == 4 ? 5 : P.hash_type;
+  const uint32_t mb = (P.abs_base >= P.max_backward) ? P.max_backward : bmin(pos + P.abs_base, P.max_backward);
+  uint32_t key = 0, clen = 0;
+  if (lane < (uint32_t)NL) {
+    const int32_t back = cache_candidate(dca, (int)lane);
+    if (back > 0 && (uint32_t)back <= mb) {
+      const uint64_t x = ldu64(data + pos) ^ ldu64(data + pos - back);
+      uint32_t len = x ? ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : CAPA;
+      len = bmin(len, maxl);
+      if (len == CAPA && maxl > CAPA) len = lane_lcp_ext(data + pos, (uint32_t)back, CAPA, maxl);
+      if (len >= 3 || (len == 2 && lane < 2)) {
+        clen = len;
+        if (NL == 4) key = (score_last_distance(5, len, lane) << 2) | (3u - lane);
+        else {
+          const uint32_t bonus = len == maxl ? score_last_distance(ht, 0, lane) - 1880u : 0u;
+          key = ((len << 12) | (bonus << 4) | (15u - lane)) + 1u;
+        }
+      }
+    }
+  }
+  key = __reduce_max_sync(FULL, key);
+  bool found = key != 0;
+  uint32_t f_len = 0, f_dist = 0, f_score = BRO_MIN_SCORE;
+  if (found) {
+    if (NL == 4) {
+      const uint32_t wi = 3u - (key & 3u);
+      f_len = __shfl_sync(FULL, clen, (int)wi);
+      f_dist = (uint32_t)cache_candidate(dca, (int)wi);
+      f_score = key >> 2;
+    } else {
+      const uint32_t wi = 15u - ((key - 1u) & 15u);
+      f_len = (key - 1u) >> 12;
+      f_dist = (uint32_t)cache_candidate(dca, (int)wi);
+      f_score = score_last_distance(ht, f_len, wi);
+    }
+  }
+  const uint32_t b = deep_best_warp<DEPTH>(A, P.abs_base + pos, rank, s_back);
+  const uint32_t blen = b & 0xFFu;
+  if (b & BRO_BEST_DICT) {
+    Match dm;
+    if (!found && D && dict_decode(b, ht, maxl, mb, &dm)) { found = true; f_len = dm.len; f_dist = dm.dist; f_score = dm.score; }
+  } else if (blen != 0) {
+    const uint32_t bdist = b >> 8;
+    uint32_t len = bmin(blen, maxl);
+    if (blen >= P.lcap && maxl > len) len = warp_lcp_ext(data + pos, bdist, len, maxl);
+    if (len >= 4) {
+      const uint32_t score = score_regular(ht, len, bdist);
+      if (f_score < score) { f_score = score; f_len = len; f_dist = bdist; found = true; }
+    }
+  }
+  out->len = f_len; out->dist = f_dist; out->score = f_score;
+  return found;
+}
+
+template <int NL, int DEPTH>
+__device__ __forceinline__ uint32_t parse_range_ondemand(const EncParams& P, const DeepArgs& A, const uint8_t* data, uint32_t rstart,
+                                                         uint32_t rend, RawCmd* out, uint32_t* tail, uint32_t* ncopy, bool D, int32_t* dc,
+                                                         uint32_t* s_back) {
+  const uint32_t FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t htl = P.hash_type == 6 ? 8u : 4u;
+  const uint32_t window = P.quality < 9 ? 64u : 512u;
+  const uint32_t uend = rend;
+  uint32_t pos = rstart, insert_len = 0, ncmd = 0, copied = 0;
+  uint32_t arh = pos + window;
+  // ranks of 32 consecutive positions ride in the lanes: the walk mostly moves a few bytes at a time
+  uint32_t rk_base = 0x80000000u, rk_val = 0;  // (no position is that large: the first query loads)
+  auto rank_of = [&](uint32_t q) -> uint32_t {
+    if (q - rk_base >= 32u) {
+      rk_base = q;
+      rk_val = q + lane < P.n ? __ldg(A.m.best + P.abs_base + q + lane) : 0u;
+    }
+    return __shfl_sync(FULL, rk_val, (int)(q - rk_base));
+  };
+  while (pos + htl < uend) {
+    uint32_t max_len = uend - pos;
+    Match m;
+    if (find_match_ondemand<NL, DEPTH>(P, A, data, dc, pos, max_len, D, rank_of(pos), s_back, &m)) {
+      int delayed = 0;
+      max_len--;
+      for (;; max_len--) {
+        Match m2;
+        const bool f2 = find_match_ondemand<NL, DEPTH>(P, A, data, dc, pos + 1, max_len, D, rank_of(pos + 1), s_back, &m2);
+        if (f2 && m2.score >= m.score + 175u) {
+          pos++;
+          insert_len++;
+          m = m2;
+          if (++delayed < 4 && pos + htl < uend) continue;
+        }
+        break;
+      }
+      const uint32_t mlen = len_bytes(m.len);
+      arh = pos + 2 * mlen + window;
+      if (!len_is_dict(m.len) && (int32_t)m.dist != dc[0]) { dc[3] = dc[2]; dc[2] = dc[1]; dc[1] = dc[0]; dc[0] = (int32_t)m.dist; }
+      if (out && lane < 3) reinterpret_cast<uint32_t*>(out + ncmd)[lane] = lane == 0 ? insert_len : (lane == 1 ? m.len : m.dist);
+      ++ncmd;
+      insert_len = 0;
+      copied += mlen;
+      pos += mlen;
+    } else {
+      insert_len++;
+      pos++;
+      if (pos > arh) {
+        const uint32_t margin = bmax(htl - 1u, 4u);
+        if (pos + 16 + margin >= uend) { insert_len += uend - pos; pos = uend; }
+        else if (pos > arh + 4 * window) { insert_len += 16; pos += 16; }
+        else { insert_len += 8; pos += 8; }
+      }
+    }
+  }
+  insert_len += uend - pos;
+  *tail = insert_len;
+  *ncopy = copied;
+  return ncmd;
+}
+
+template <int NL, int DEPTH>
+__global__ void __launch_bounds__(PARSE_WARPS * 32) k_parse_ondemand(Workspace W, DeepArgs A) {
+  const uint32_t u = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);
+  if (u >= W.num_units) return;
+  const EncParams& P = W.P;
+  const uint32_t s = u * P.unit, e = bmin(P.n, s + P.unit);
+  uint32_t tail = 0, ncopy = 0, ncmd = 0;
+  const bool D = P.use_dict != 0;
+  int32_t dc[4] = {0x3fffffff, 0x3fffffff, 0x3fffffff, 0x3fffffff};
+  const bool warm = (u % P.mb_units) != 0 && s >= BRO_WARMUP_BYTES;
+  RawCmd* const out = W.raw + (size_t)u * (P.unit / 2 + 1);
+  __shared__ uint32_t s_back_all[PARSE_WARPS][256];
+  for (int phase = warm ? 0 : 1; phase < 2; ++phase) {
+    const uint32_t rs = phase ? s : s - BRO_WARMUP_BYTES, re = phase ? e : s;
+    ncmd = parse_range_ondemand<NL, DEPTH>(P, A, W.data, rs, re, phase ? out : nullptr, &tail, &ncopy, D, dc, s_back_all[threadIdx.x >> 5]);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    W.unit_ncmd[u] = ncmd;
+    W.unit_tail[u] = tail;
+    W.unit_ncopy[u] = ncopy;
+  }
+}
+
 #ifndef PARSE_MIN_BLOCKS
 #define PARSE_MIN_BLOCKS 10
 #endif

@@ -66,7 +66,6 @@ def test_custom_dictionary_and_abi_details():
         h = L.BrotliEncoderCreateInstance(None, None, None)
         assert h
         assert L.BrotliEncoderSetParameter(h, rb.BROTLI_PARAM_QUALITY, 5)
-        assert not L.BrotliEncoderSetParameter(h, rb.BROTLI_PARAM_CATABLE, 1)  # refused, not ignored
         assert not L.BrotliEncoderSetParameter(h, rb.BROTLI_PARAM_LARGE_WINDOW, 1)
         if use_dict:
             L.BrotliEncoderSetCustomDictionary(h, len(dictionary), dictionary)
@@ -286,6 +285,76 @@ def test_device_resident_io(encoder):
     c = bytes(t_out[:n].cpu().numpy())
     assert sys_decompress(c, len(d)) == d
     assert c == encoder.compress(d, 5, 22)
+
+
+# ---- stream framing parameters: catable / appendable / magic_number / byte_align / bare_stream ----
+
+def _framed(data, q=5, lgwin=22, **kw):
+    import rust_brotli_b200 as rb
+    w = io.BytesIO()
+    rb.BrotliCompress(io.BytesIO(data), w, rb.BrotliEncoderParams(quality=q, lgwin=lgwin, **kw))
+    return w.getvalue()
+
+
+@pytest.mark.parametrize("q", [5, 9, 10])
+def test_catable_streams_stitch_like_brocatli(q):
+    """BROTLI_PARAM_CATABLE (encode.rs:264-272, :2285-2333): the stream starts with its first two bytes as an uncompressed
+    metablock, uses no static dictionary and ends with an empty last metablock, so the reference's BroCatli
+    (src/concat/mod.rs, restated in tests/brocatli_ref.py) can splice it behind any other stream."""
+    import brocatli_ref as bc
+    a, b, c = golden_bytes("alice29.txt")[:90000], golden_bytes("asyoulik.txt")[:70000], golden_bytes("random_then_unicode")[:60000]
+    sa = _framed(a, q, catable=True, magic_number=True)
+    sb = _framed(b, q, catable=True)
+    sc = _framed(c, q, catable=True, byte_align=True)
+    for s, d in ((sa, a), (sb, b), (sc, c)):
+        assert sys_decompress(s, len(d)) == d  # each is a complete stream on its own
+        off = bc.first_metablock_aligned_offset(s)  # raises unless the stream starts with a metadata / uncompressed metablock
+        assert off % 8 in (0, 1, 2, 3, 4, 5, 6, 7)
+    # 4 window bits + 14 header bits of the metadata metablock, padded to 3 bytes; then e1 97 81 (catable), VERSION 1, size hint
+    assert bytes(sa[3:6]) == b"\xe1\x97\x81" and sa[6] == 1
+    assert sc[-1] == 3  # byte_align: padding metablock, then ISLAST + ISLASTEMPTY alone in the last byte
+    whole = bc.concat([sa, sb, sc, _framed(b"", q, catable=True), sb])
+    assert sys_decompress(whole, len(a) + 2 * len(b) + len(c)) == a + b + c + b
+    with pytest.raises(bc.NotCraftedForConcatenation):  # a plain stream starts with a compressed metablock: the stitcher refuses it
+        bc.concat([sa, _framed(b, q)])
+
+
+def test_bare_and_appendable_streams_concatenate_by_memcpy():
+    """bare_stream (encode.rs:277-282, :676, :1937): no window bits (with catable), no final metablock, byte aligned -- pieces
+    are glued with memcpy behind a header-carrying first piece and closed with the single byte 0x03.  appendable + byte_align:
+    strip that last byte and keep appending."""
+    a, b, c = golden_bytes("alice29.txt")[:50000], golden_bytes("asyoulik.txt")[:40000], b"tail " * 2000
+    head = _framed(a, 5, appendable=True, byte_align=True)
+    assert head[-1] == 3 and sys_decompress(head, len(a)) == a
+    mid = _framed(b, 5, catable=True, bare_stream=True)
+    end = _framed(c, 9, catable=True, bare_stream=True)
+    glued = head[:-1] + mid + end + b"\x03"
+    assert sys_decompress(glued, len(a) + len(b) + len(c)) == a + b + c
+    # bare without catable keeps the window bits: it is a first piece
+    first = _framed(a, 5, bare_stream=True)
+    assert sys_decompress(first + mid + b"\x03", len(a) + len(b)) == a + b
+
+
+def test_framing_small_and_empty_inputs():
+    import brocatli_ref as bc
+    for d in (b"", b"x", b"xy", b"xyz", b"hello hello hello hello"):
+        for kw in (dict(catable=True), dict(catable=True, magic_number=True), dict(appendable=True, byte_align=True),
+                   dict(magic_number=True), dict(catable=True, byte_align=True)):
+            s = _framed(d, 5, **kw)
+            assert sys_decompress(s, max(1, len(d))) == d, (d, kw)
+        s2 = bc.concat([_framed(b"abc", 5, catable=True), _framed(d, 5, catable=True)])
+        assert sys_decompress(s2, 3 + len(d)) == b"abc" + d
+
+
+def test_compress_multi_honours_framing():
+    """CompressMulti with catable + magic_number: prologue of shard 0, trailer of the last shard; still one valid stream."""
+    import rust_brotli_b200 as rb
+    import brocatli_ref as bc
+    d = golden_bytes("alice29.txt")
+    c = rb.compress_multi(rb.BrotliEncoderParams(quality=5, lgwin=22, catable=True, magic_number=True, byte_align=True), d, 4)
+    assert sys_decompress(c, len(d)) == d
+    assert bytes(c[3:6]) == b"\xe1\x97\x81" and c[-1] == 3
+    assert sys_decompress(bc.concat([c, c]), 2 * len(d)) == d + d
 
 
 # ---- BASELINE.json configs at their full per-GPU sizes: size-independent properties (round trip, size bounds) ----

@@ -140,3 +140,45 @@ def test_model_static_dictionary_reaches_libbrotlienc_on_english(model):
     ref = len(sys_compress(d, 5, 20))
     assert sys_decompress(on, len(d)) == d and sys_decompress(off, len(d)) == d
     assert len(on) <= ref * 1.005 < len(off)
+
+
+def _catable_from_model(model, d, q, lgwin=22, byte_align=False):
+    """The framing csrc/bro_capi.cu:compress_framed builds around a catable stream, assembled here from the CPU model's ranges:
+    window bits, the first two bytes as an uncompressed metablock, the rest without static dictionary, empty last metablock."""
+    bits = []
+    def put(n, v):
+        bits.extend((v >> i) & 1 for i in range(n))
+    put(4, ((lgwin - 17) << 1) | 1)
+    n2 = min(2, len(d))
+    if n2:
+        put(1, 0); put(2, 0); put(16, n2 - 1); put(1, 1)
+        bits.extend([0] * (-len(bits) % 8))
+        for byte in d[:n2]:
+            put(8, byte)
+    head = bytes(sum(bits[i + j] << j for j in range(8)) for i in range(0, len(bits) - len(bits) % 8, 8))
+    if len(d) <= 2:
+        tail_bits = bits[len(head) * 8:] + [1, 1]
+        tail_bits += [0] * (-len(tail_bits) % 8)
+        return head + bytes(sum(tail_bits[i + j] << j for j in range(8)) for i in range(0, len(tail_bits), 8))
+    if byte_align:
+        body, _ = model.compress_range(d, 2, len(d) - 2, q, lgwin, False, False, True, use_dict=0)
+        return head + body + b"\x03"
+    body, _ = model.compress_range(d, 2, len(d) - 2, q, lgwin, False, True, False, use_dict=0)
+    return head + body
+
+
+@pytest.mark.parametrize("q", [5, 10])
+def test_catable_framing_stitches_like_brocatli(model, q):
+    """Streams framed as BROTLI_PARAM_CATABLE asks (encode.rs:2285-2333) go through the restated BroCatli splice
+    (tests/brocatli_ref.py, src/concat/mod.rs) and decode to the concatenated inputs; a plain stream is refused by it."""
+    import brocatli_ref as bc
+    a, b = golden_bytes("alice29.txt")[:40000], golden_bytes("asyoulik.txt")[:30000]
+    sa, sb, se, s1 = (_catable_from_model(model, a, q), _catable_from_model(model, b, q, byte_align=True),
+                      _catable_from_model(model, b"", q), _catable_from_model(model, b"z", q))
+    for s, d in ((sa, a), (sb, b), (se, b""), (s1, b"z")):
+        assert sys_decompress(s, max(1, len(d))) == d
+    whole = bc.concat([sa, sb, se, s1, sa])
+    assert sys_decompress(whole, 2 * len(a) + len(b) + 1) == a + b + b"z" + a
+    with pytest.raises(bc.NotCraftedForConcatenation):
+        bc.concat([sa, model.compress(b, q, 22)[0]])
+    assert bc.window_bits(sa) == (22, 4)
