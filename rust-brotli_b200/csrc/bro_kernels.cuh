@@ -1531,7 +1531,33 @@ __global__ void __launch_bounds__(256) k_rank_sig(MatchArgs a, uint32_t* sig) {
 //      best so far is dropped after one byte, and a full-length match ends the search (both exact: a farther candidate that is
 //      not longer cannot score higher, score_regular is monotone in both).
 template <int DEPTH>
-__device__ __forceinline__ uint32_t deep_best_warp(const DeepArgs& A, uint32_t p, uint32_t r, uint32_t* s_back) {
+__device__ __forceinline__ void deep_fetch(const DeepArgs& A, uint32_t r, uint32_t* cpos, uint32_t* csig) {  // phase 1 loads
+  const uint32_t lane = threadIdx.x & 31;
+#pragma unroll
+  for (int t = 0; t < DEPTH / 32; ++t) {
+    const uint32_t k = (uint32_t)t * 32u + lane;
+    cpos[t] = 0; csig[t] = 0;
+    if (r >= k + 1u) {
+      const uint32_t j = r - 1u - k;
+      cpos[t] = __ldg(A.m.sorted + j);
+      csig[t] = __ldg(A.sig + j);
+    }
+  }
+}
+// L2 prefetch of the candidate lines of a position that will probably be asked for next
+template <int DEPTH>
+__device__ __forceinline__ void deep_prefetch(const DeepArgs& A, uint32_t r) {
+  constexpr uint32_t T = DEPTH / 32;
+  const uint32_t lane = threadIdx.x & 31;
+  if (lane < 2u * (T + 1u)) {
+    const uint32_t* base = lane <= T ? A.m.sorted : A.sig;
+    const uint32_t line = lane <= T ? lane : lane - (T + 1u);
+    if (r >= 32u * line + 1u) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (r - 1u - 32u * line)));
+  }
+}
+template <int DEPTH>
+__device__ __forceinline__ uint32_t deep_best_warp(const DeepArgs& A, uint32_t p, uint32_t r, const uint32_t* cpos, const uint32_t* csig,
+                                                   uint32_t* s_back) {
   constexpr int T = DEPTH / 32;
   const MatchArgs& a = A.m;
   const uint32_t FULL = 0xffffffffu;
@@ -1544,17 +1570,6 @@ __device__ __forceinline__ uint32_t deep_best_warp(const DeepArgs& A, uint32_t p
   const uint32_t maxl = bmin(a.lcap, a.n - p);
   const uint32_t mbk = bmin(p, a.max_backward);
   const uint32_t kNone = (BRO_MIN_SCORE << 16) | 0xFFFFu;
-  uint32_t cpos[T], csig[T];
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    const uint32_t k = (uint32_t)t * 32u + lane;
-    cpos[t] = 0; csig[t] = ~mysig;
-    if (r >= k + 1u) {
-      const uint32_t j = r - 1u - k;
-      cpos[t] = __ldg(a.sorted + j);
-      csig[t] = __ldg(A.sig + j);
-    }
-  }
   uint32_t S = 0;  // survivors so far
   __syncwarp();
 #pragma unroll
@@ -1612,11 +1627,15 @@ __device__ __forceinline__ uint32_t deep_best_warp(const DeepArgs& A, uint32_t p
 // find_match() of bro_parse.cuh at the range-relative position pos, whole warp: lane i probes cached distance i, then the bucket
 template <int NL, int DEPTH>
 __device__ __forceinline__ bool find_match_ondemand(const EncParams& P, const DeepArgs& A, const uint8_t* data, const int32_t* dca,
-                                                    uint32_t pos, uint32_t maxl, bool D, uint32_t rank, uint32_t* s_back, Match* out) {
+                                                    uint32_t pos, uint32_t maxl, bool D, uint32_t rank, uint32_t rank_next,
+                                                    uint32_t* s_back, Match* out) {
   constexpr uint32_t CAPA = 8;
   const uint32_t FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x & 31;
   const int ht = NL == 4 ? 5 : P.hash_type;
+  uint32_t cpos[DEPTH / 32], csig[DEPTH / 32];
+  deep_fetch<DEPTH>(A, rank, cpos, csig);   // in flight while the cached distances are probed
+  deep_prefetch<DEPTH>(A, rank_next);
   const uint32_t mb = (P.abs_base >= P.max_backward) ? P.max_backward : bmin(pos + P.abs_base, P.max_backward);
   uint32_t key = 0, clen = 0;
   if (lane < (uint32_t)NL) {
@@ -1652,7 +1671,7 @@ __device__ __forceinline__ bool find_match_ondemand(const EncParams& P, const De
       f_score = score_last_distance(ht, f_len, wi);
     }
   }
-  const uint32_t b = deep_best_warp<DEPTH>(A, P.abs_base + pos, rank, s_back);
+  const uint32_t b = deep_best_warp<DEPTH>(A, P.abs_base + pos, rank, cpos, csig, s_back);
   const uint32_t blen = b & 0xFFu;
   if (b & BRO_BEST_DICT) {
     Match dm;
@@ -1681,24 +1700,30 @@ __device__ __forceinline__ uint32_t parse_range_ondemand(const EncParams& P, con
   const uint32_t uend = rend;
   uint32_t pos = rstart, insert_len = 0, ncmd = 0, copied = 0;
   uint32_t arh = pos + window;
-  // ranks of 32 consecutive positions ride in the lanes: the walk mostly moves a few bytes at a time
-  uint32_t rk_base = 0x80000000u, rk_val = 0;  // (no position is that large: the first query loads)
+  // ranks of 64 consecutive positions ride in the lanes (two registers): the walk mostly moves a few bytes at a time, and the
+  // second half is reloaded one half ahead of its use
+  uint32_t rk_base = 0x80000000u, rk0 = 0, rk1 = 0;  // (no position is that large: the first query loads)
+  auto rank_load = [&](uint32_t q) -> uint32_t { return q + lane < P.n ? __ldg(A.m.best + P.abs_base + q + lane) : 0u; };
   auto rank_of = [&](uint32_t q) -> uint32_t {
-    if (q - rk_base >= 32u) {
-      rk_base = q;
-      rk_val = q + lane < P.n ? __ldg(A.m.best + P.abs_base + q + lane) : 0u;
-    }
-    return __shfl_sync(FULL, rk_val, (int)(q - rk_base));
+    uint32_t d = q - rk_base;
+    if (d >= 64u) { rk_base = q; rk0 = rank_load(q); rk1 = rank_load(q + 32u); d = 0; }
+    else if (d >= 32u) { rk_base += 32u; rk0 = rk1; rk1 = rank_load(rk_base + 32u); d -= 32u; }
+    return __shfl_sync(FULL, rk0, (int)d);
+  };
+  auto rank_peek = [&](uint32_t q) -> uint32_t {  // rank of a position inside the window (0 outside: prefetch only)
+    const uint32_t d = q - rk_base;
+    const uint32_t v0 = __shfl_sync(FULL, rk0, (int)(d & 31u)), v1 = __shfl_sync(FULL, rk1, (int)(d & 31u));
+    return d < 32u ? v0 : (d < 64u ? v1 : 0u);
   };
   while (pos + htl < uend) {
     uint32_t max_len = uend - pos;
     Match m;
-    if (find_match_ondemand<NL, DEPTH>(P, A, data, dc, pos, max_len, D, rank_of(pos), s_back, &m)) {
+    if (find_match_ondemand<NL, DEPTH>(P, A, data, dc, pos, max_len, D, rank_of(pos), rank_peek(pos + 1), s_back, &m)) {
       int delayed = 0;
       max_len--;
       for (;; max_len--) {
         Match m2;
-        const bool f2 = find_match_ondemand<NL, DEPTH>(P, A, data, dc, pos + 1, max_len, D, rank_of(pos + 1), s_back, &m2);
+        const bool f2 = find_match_ondemand<NL, DEPTH>(P, A, data, dc, pos + 1, max_len, D, rank_of(pos + 1), rank_peek(pos + 2), s_back, &m2);
         if (f2 && m2.score >= m.score + 175u) {
           pos++;
           insert_len++;

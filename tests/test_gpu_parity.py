@@ -287,6 +287,34 @@ def test_device_resident_io(encoder):
     assert c == encoder.compress(d, 5, 22)
 
 
+@pytest.mark.parametrize("q,lgwin", [(9, 22), (8, 22), (7, 22), (9, 16), (5, 16)])
+def test_deep_buckets_on_demand_equals_up_front_and_model(encoder, model, q, lgwin):
+    """q7..q9 (and lgwin <= 16): the deep bucket lists are searched either for every position up front (k_match_deep + k_parse)
+    or on demand where the greedy / lazy walk stands (k_rank_sig + k_parse_ondemand, the reference's own shape:
+    FindLongestMatch at the visited positions, backward_references/mod.rs:2376-2552).  Both must give the stream of the CPU
+    model, bit for bit -- text, JSON logs and a tail shorter than a unit."""
+    import rust_brotli_b200 as rb
+    from tools import datagen
+    d = datagen.enwik_like(3_000_000) + datagen.json_logs(2_500_000) + golden_bytes("random_then_unicode")[:70001]
+    outs = []
+    try:
+        for mode in (0, 2):
+            encoder.set_option(rb._native.OPT_ONDEMAND, mode)
+            outs.append(encoder.compress(d, q, lgwin))
+    finally:
+        encoder.set_option(rb._native.OPT_ONDEMAND, 1)
+    assert outs[0] == outs[1]
+    assert outs[0] == model.compress(d, q, lgwin)[0]
+    assert sys_decompress(outs[0], len(d)) == d
+    small = golden_bytes("alice29.txt")  # default rule: a few units stay on the up-front path; forced on demand must agree too
+    encoder.set_option(rb._native.OPT_ONDEMAND, 2)
+    try:
+        forced = encoder.compress(small, q, lgwin)
+    finally:
+        encoder.set_option(rb._native.OPT_ONDEMAND, 1)
+    assert forced == encoder.compress(small, q, lgwin) == model.compress(small, q, lgwin)[0]
+
+
 # ---- stream framing parameters (SURVEY 8f-2): catable / appendable / magic_number / byte_align / bare_stream ----
 
 def _framed(data, q=5, lgwin=22, **kw):
