@@ -111,7 +111,7 @@ struct B200Encoder {
   bool ok = false;
   // configuration knobs (tests flip these)
   uint32_t unit = 4096, mb_units = 1024, lcap = 64;
-  int use_rle_opt = 1, split = 1, ctx_model = 1, use_dict = 1, hq_split = 1;
+  int use_rle_opt = 1, split = 1, ctx_model = 1, use_dict = 1, hq_split = 1, hq_levels = HQ_MAX_LEVELS;
   uint32_t hq_unit = 16384;  // parse unit of the shortest-path parse (quality >= 10)
   int hq_thread_units = 0;   // 1: one parse unit per thread instead of one per warp (A/B switch)
   int num_lanes = 4;
@@ -211,6 +211,7 @@ struct B200Encoder {
     P->ctx_model = ctx_model;
     P->use_dict = use_dict;
     P->hq_split = hq_split;
+    P->hq_levels = quality >= 10 ? hq_levels : 0;
     if (quality >= 10) {  // same metablock span, larger parse units
       const uint32_t span = P->unit * P->mb_units;
       P->unit = bmin(hq_unit, span);
@@ -543,8 +544,28 @@ struct B200Encoder {
         aa.hqm = W.hqm - (size_t)range_start * HQ_MAXM;
         aa.hqn = W.hqn - range_start;
         aa.quality = P.quality;
+        aa.level = 0;
+        aa.last_pass = P.hq_levels == 0;
         if (P.depth != 1024) { fprintf(stderr, "[brotli_b200] unsupported bucket depth %d\n", P.depth); return false; }
         k_match_all<1024><<<mgrid, MATCH_THREADS, (size_t)(MATCH_THREADS + 1024) * 3 * 4, stream>>>(aa);
+        for (int lv = 0; lv < P.hq_levels; ++lv) {  // long-prefix levels: the batch re-sorted by the level's hash, lists merged
+          SortArgs sl = sa;
+          sl.hash_type = BRO_HASH_LEVEL0 + lv;
+          for (int pass = 0; pass < 2; ++pass) {
+            sl.pass = pass;
+            sl.in = pass == 0 ? nullptr : L.d_sortA.as<uint32_t>();
+            sl.outw = pass == 0 ? L.d_sortA.as<uint32_t>() : L.d_sortB.as<uint32_t>();
+            k_sort_hist<<<tiles, SORT_THREADS, 0, stream>>>(sl);
+            k_scan_rows<<<256, 256, 0, stream>>>(sl.hist, tiles, L.d_digit.as<uint32_t>() + 256);
+            k_scan_digits<<<1, 256, 0, stream>>>(L.d_digit.as<uint32_t>() + 256, L.d_digit.as<uint32_t>());
+            k_sort_scatter<<<tiles, SORT_THREADS, 0, stream>>>(sl);
+            launches += 4;
+          }
+          aa.level = lv;
+          aa.last_pass = lv + 1 == P.hq_levels;
+          k_match_level<HQ_LEVEL_DEPTH><<<mgrid, MATCH_THREADS, (size_t)(MATCH_THREADS + HQ_LEVEL_DEPTH) * 3 * 4, stream>>>(aa);
+          launches += 1;
+        }
       } else
       switch (P.depth) {  // bucket depth = 1 << block_bits: 16 (q5) .. 256 (q9, and lgwin <= 16)
         case 16:
@@ -690,6 +711,7 @@ int b200_encoder_set_option(B200Encoder* e, int option, uint32_t value) {
     case B200_OPT_SHALLOW_MATCH: e->shallow_match = (int)value; return 1;
     case B200_OPT_PAIR_PARSE: e->pair_parse = (int)value; return 1;
     case B200_OPT_ONDEMAND: e->ondemand = (int)value; return 1;
+    case B200_OPT_HQ_LEVELS: e->hq_levels = value > HQ_MAX_LEVELS ? HQ_MAX_LEVELS : (int)value; return 1;
     case B200_OPT_HQ_SPLIT: e->hq_split = (int)value; return 1;
     case B200_OPT_HQ_UNIT: e->hq_unit = value; return 1;
     case B200_OPT_HQ_THREAD_UNITS: e->hq_thread_units = (int)value; return 1;

@@ -210,23 +210,32 @@ struct SortArgs {
   int pass;
 };
 
+#define BRO_HASH_LEVEL0 100  // hash_type 100 + l: the long-prefix level l of quality 10 / 11 (bro_hq.cuh: 8, 16, 32 bytes)
 __device__ __forceinline__ uint32_t smem_key(const uint32_t* sw, uint32_t e, int hash_type, int key_bits) {
   // bytes e..e+7 of the tile staged as little-endian words
+  const uint32_t sh = (e & 3u) * 8u;
+  if (hash_type >= BRO_HASH_LEVEL0) {
+    const uint32_t* q = sw + (e >> 2);
+    const uint64_t h = hq_level_hash_with([q, sh](uint32_t k) {
+      const uint32_t w0 = q[k >> 2], w1 = q[(k >> 2) + 1], w2 = q[(k >> 2) + 2];
+      return ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
+    }, hq_level_bytes(hash_type - BRO_HASH_LEVEL0));
+    return hq_level_key(h, key_bits);
+  }
   uint32_t w0 = sw[e >> 2], w1 = sw[(e >> 2) + 1], w2 = sw[(e >> 2) + 2];
-  uint32_t sh = (e & 3u) * 8u;
   uint32_t lo = __funnelshift_r(w0, w1, sh);
   uint32_t hi = __funnelshift_r(w1, w2, sh);
   return hash_key_from_words(hash_type, key_bits, lo, hi);
 }
 
 __device__ __forceinline__ void sort_stage_tile(const SortArgs& a, uint32_t tile, uint32_t* sw, uint64_t* bar) {
-  // stage SORT_TILE + 16 bytes with one TMA bulk copy (the input is padded, so reading past `count` is safe; the batch origin
+  // stage SORT_TILE + 48 bytes with one TMA bulk copy (the input is padded, so reading past `count` is safe; the batch origin
   // is 4096-byte aligned)
-  tma_stage_tile(sw, a.data + (size_t)tile * SORT_TILE, SORT_TILE + 16, bar);
+  tma_stage_tile(sw, a.data + (size_t)tile * SORT_TILE, SORT_TILE + 48, bar);
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(SortArgs a) {
-  __shared__ __align__(16) uint32_t sw[SORT_TILE / 4 + 4];
+  __shared__ __align__(16) uint32_t sw[SORT_TILE / 4 + 12];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t sh[256];
   const uint32_t tile = blockIdx.x;
@@ -290,7 +299,7 @@ __global__ void __launch_bounds__(256) k_scan_digits(const uint32_t* totals, uin
 }
 
 __global__ void __launch_bounds__(SORT_THREADS, 6) k_sort_scatter(SortArgs a) {
-  __shared__ __align__(16) uint32_t sw[SORT_TILE / 4 + 4];
+  __shared__ __align__(16) uint32_t sw[SORT_TILE / 4 + 12];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t wc[SORT_THREADS / 32][256];
   __shared__ uint32_t s_word[SORT_TILE];  // element words parked in shared memory (keeps the register count low => occupancy)

@@ -24,6 +24,8 @@ struct MatchAllArgs {
   HqMatch* hqm;     // indexed by absolute position (pre-shifted by the range start)
   uint8_t* hqn;
   int quality;
+  int level;        // k_match_level: which long-prefix level this pass serves
+  int last_pass;    // the pass that adds the static-dictionary matches (they come after every window match)
 };
 
 template <int DEPTH>
@@ -70,10 +72,71 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_all(MatchAllArgs A) {
         if (!hq_bucket_candidate(cur, backward, maxl, L)) break;
       }
     }
-    if (a.use_dict) hq_dict_matches(a.dict, cur, a.n - p, L);
+    if (a.use_dict && A.last_pass) hq_dict_matches(a.dict, cur, a.n - p, L);
   }
   A.hqn[p] = (uint8_t)L.n;
   HqMatch* out = A.hqm + (size_t)p * HQ_MAXM;
+  for (uint32_t k = 0; k < L.n; ++k) out[k] = L.m[k];
+}
+
+// One long-prefix level (bro_hq.cuh): the batch has been sorted by the 15-bit key of the level's hash; a thread scans the
+// HQ_LEVEL_DEPTH entries in front of its own, keeps those whose 32 check bits agree, builds the level's Pareto front and merges
+// it into the list the earlier passes left in hqm / hqn.
+template <int DEPTH>
+__global__ void __launch_bounds__(MATCH_THREADS) k_match_level(MatchAllArgs A) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  __shared__ __align__(8) uint64_t s_bar;
+  const MatchArgs& a = A.m;
+  constexpr uint32_t E = MATCH_THREADS + (uint32_t)DEPTH;
+  uint32_t* s_pos = smem;
+  uint32_t* s_key = smem + E;
+  uint32_t* s_chk = smem + 2 * E;
+  const uint32_t nb8 = hq_level_bytes(A.level);
+  const int64_t j0 = (int64_t)blockIdx.x * MATCH_THREADS - DEPTH;
+  match_stage_positions(a, j0, E, s_pos, &s_bar);
+  for (uint32_t i = threadIdx.x; i < E; i += MATCH_THREADS) {
+    const uint32_t pos = s_pos[i];
+    uint32_t key = 0xFFFFFFFFu, chk = 0;
+    if (pos != 0xFFFFFFFFu) {
+      const uint8_t* q = a.data + a.origin + pos;
+      const uint64_t h = hq_level_hash_with([q](uint32_t k) { return ldu64(q + k); }, nb8);
+      key = hq_level_key(h, a.key_bits);
+      chk = (uint32_t)h;
+    }
+    s_key[i] = key; s_chk[i] = chk;
+  }
+  __syncthreads();
+  const uint32_t i = threadIdx.x + (uint32_t)DEPTH;
+  const uint32_t prel = s_pos[i];
+  if (prel == 0xFFFFFFFFu || prel < a.payload_begin) return;
+  const uint32_t p = a.origin + prel;
+  const bool search = a.n - p >= nb8 + 8u;
+  if (!search && !(A.last_pass && a.use_dict && a.n - p >= 8)) return;  // nothing to add to this position's list
+  const uint8_t* cur = a.data + p;
+  const uint32_t maxl = bmin(a.lcap, a.n - p);
+  const uint32_t max_backward = bmin(p, a.max_backward);
+  HqMatch* out = A.hqm + (size_t)p * HQ_MAXM;
+  HqMatchList L;
+  L.n = A.hqn[p];
+  L.best_len = 1;
+  for (uint32_t k = 0; k < L.n; ++k) L.m[k] = out[k];
+  if (L.n) L.best_len = L.m[L.n - 1].lc & 0xFFFFu;
+  if (search) {
+    HqMatchList B;
+    hq_list_init(B);
+    const uint32_t key = s_key[i], chk = s_chk[i];
+    for (uint32_t c = 1; c <= (uint32_t)DEPTH; ++c) {
+      const uint32_t ci = i - c;
+      if (s_key[ci] != key) break;
+      const uint32_t backward = prel - s_pos[ci];
+      if (backward > max_backward) break;
+      if (s_chk[ci] != chk) continue;
+      if (!hq_bucket_candidate(cur, backward, maxl, B)) break;
+    }
+    hq_merge_lists(L, B);
+  }
+  if (a.use_dict && A.last_pass && a.n - p >= 8) hq_dict_matches(a.dict, cur, a.n - p, L);
+  A.hqn[p] = (uint8_t)L.n;
   for (uint32_t k = 0; k < L.n; ++k) out[k] = L.m[k];
 }
 

@@ -41,6 +41,7 @@ struct EncParams {
   int ctx_model;      // literal context modelling on/off
   int use_dict;       // static-dictionary matches on/off
   int hq_split;       // quality >= 10: 1 = BrotliSplitBlock + clustered context maps (default), 0 = the greedy splitter of q5..q9
+  int hq_levels;      // quality >= 10: number of long-prefix candidate levels (8, 16, 32 bytes) on top of the 4-byte buckets: 0..3
 };
 
 // ---- scores ----
