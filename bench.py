@@ -33,8 +33,8 @@ ALG_BYTES_PER_POS_MATCH = 9  # 1 B input + 4 B sorted position read +
 CHUNK_BYTES = 24 << 20       # one k_match launch per chunk (csrc/bro_parse.cuh BRO_CHUNK_BYTES)
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_match launch (24 MiB chunk + 4 MiB halo) from the ncu --set full
 # capture summarised in profiles/ (None until a capture of the current kernel exists)
-NCU_MATCH_DRAM_BYTES_PER_LAUNCH = 925_193_472 + 697_299_712
-NCU_MATCH_SOURCE = "profiles/r01t_ncu_full.txt (ncu --set full, one k_match launch: 29.4 M sorted entries)"
+NCU_MATCH_DRAM_BYTES_PER_LAUNCH = 774_424_320 + 669_327_104
+NCU_MATCH_SOURCE = "profiles/r02x_ncu_q5.txt (ncu --set full, one k_match_shallow<16> launch: 29.4 M sorted entries, 25.2 M payload positions)"
 
 
 def load_peaks():
@@ -413,7 +413,8 @@ def main():
                          "peak_source": peak_src, "algorithmic_bytes_per_position": ALG_BYTES_PER_POS_MATCH,
                          "launch_ms": round(match_ms / max(1, -(-NB // CHUNK_BYTES)), 4),
                          "timed": "CUDA events on the launching stream, chunks serialised on one lane (K extra steps after the value loop)"},
-            # the parse has the larger share of the step (profiles/r01n: 28 % vs 21 %) but is latency / issue bound, not a memory kernel
+            # the parse has the larger share of the serialised step (profiles/r02q: 31.5 % vs 27.6 %) but is latency bound (15.8 % warps
+            # active, profiles/r02x_ncu_q5.txt), not a memory kernel
             "roofline_parse": {"kernel": "k_parse", "algorithmic_bytes_per_position": 6.8,
                                "achieved": round(6.8 * NB / (stage_acc.get("parse", 0.0) / args.steps * 1e-3) / 1e9, 1) if stage_acc.get("parse") else None,
                                "unit": "GB/s", "note": "1 B input + 4 B best[] + 12 B per command (0.15 commands / byte)"},

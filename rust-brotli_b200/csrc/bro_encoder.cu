@@ -531,6 +531,7 @@ struct B200Encoder {
       ma.dict = W.dict;
       ma.use_dict = P.use_dict;
       const size_t smem = (size_t)(MATCH_THREADS + P.depth) * 6 * 4;
+      const size_t smem_sh = (size_t)(MATCH_THREADS + P.depth) * 7 * 4;  // k_match_shallow: records + TMA staging area
       mark(L, B200_ST_MATCH);
       const uint32_t mgrid = (count + MATCH_THREADS - 1) / MATCH_THREADS;
       if (od) {  // ranks into best[], signatures into the free half of the sort ping-pong
@@ -569,11 +570,11 @@ struct B200Encoder {
       } else
       switch (P.depth) {  // bucket depth = 1 << block_bits: 16 (q5) .. 256 (q9, and lgwin <= 16)
         case 16:
-          if (shallow_match) k_match_shallow<16><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
+          if (shallow_match) k_match_shallow<16><<<mgrid, MATCH_THREADS, smem_sh, stream>>>(ma);
           else k_match<16><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
           break;
         case 32:
-          if (shallow_match) k_match_shallow<32><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
+          if (shallow_match) k_match_shallow<32><<<mgrid, MATCH_THREADS, smem_sh, stream>>>(ma);
           else k_match<32><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
           break;
         case 64: k_match_deep<64><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
