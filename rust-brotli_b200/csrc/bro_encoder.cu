@@ -212,6 +212,7 @@ struct B200Encoder {
     P->use_dict = use_dict;
     P->hq_split = hq_split;
     P->hq_levels = quality >= 10 ? hq_levels : 0;
+    P->hq_warm = 1;
     if (quality >= 10) {  // same metablock span, larger parse units
       const uint32_t span = P->unit * P->mb_units;
       P->unit = bmin(hq_unit, span);
@@ -509,10 +510,10 @@ struct B200Encoder {
         sa.pass = pass;
         sa.in = pass == 0 ? nullptr : L.d_sortA.as<uint32_t>();
         sa.outw = pass == 0 ? L.d_sortA.as<uint32_t>() : L.d_sortB.as<uint32_t>();
-        k_sort_hist<<<tiles, SORT_THREADS, 0, stream>>>(sa);
+        k_sort_hist<false><<<tiles, SORT_THREADS, 0, stream>>>(sa);
         k_scan_rows<<<256, 256, 0, stream>>>(sa.hist, tiles, L.d_digit.as<uint32_t>() + 256);
         k_scan_digits<<<1, 256, 0, stream>>>(L.d_digit.as<uint32_t>() + 256, L.d_digit.as<uint32_t>());
-        k_sort_scatter<<<tiles, SORT_THREADS, 0, stream>>>(sa);
+        k_sort_scatter<false><<<tiles, SORT_THREADS, 0, stream>>>(sa);
         launches += 4;
       }
       MatchArgs ma;
@@ -531,7 +532,6 @@ struct B200Encoder {
       ma.dict = W.dict;
       ma.use_dict = P.use_dict;
       const size_t smem = (size_t)(MATCH_THREADS + P.depth) * 6 * 4;
-      const size_t smem_sh = (size_t)(MATCH_THREADS + P.depth) * 7 * 4;  // k_match_shallow: records + TMA staging area
       mark(L, B200_ST_MATCH);
       const uint32_t mgrid = (count + MATCH_THREADS - 1) / MATCH_THREADS;
       if (od) {  // ranks into best[], signatures into the free half of the sort ping-pong
@@ -556,10 +556,10 @@ struct B200Encoder {
             sl.pass = pass;
             sl.in = pass == 0 ? nullptr : L.d_sortA.as<uint32_t>();
             sl.outw = pass == 0 ? L.d_sortA.as<uint32_t>() : L.d_sortB.as<uint32_t>();
-            k_sort_hist<<<tiles, SORT_THREADS, 0, stream>>>(sl);
+            k_sort_hist<true><<<tiles, SORT_THREADS, 0, stream>>>(sl);
             k_scan_rows<<<256, 256, 0, stream>>>(sl.hist, tiles, L.d_digit.as<uint32_t>() + 256);
             k_scan_digits<<<1, 256, 0, stream>>>(L.d_digit.as<uint32_t>() + 256, L.d_digit.as<uint32_t>());
-            k_sort_scatter<<<tiles, SORT_THREADS, 0, stream>>>(sl);
+            k_sort_scatter<true><<<tiles, SORT_THREADS, 0, stream>>>(sl);
             launches += 4;
           }
           aa.level = lv;
@@ -570,11 +570,11 @@ struct B200Encoder {
       } else
       switch (P.depth) {  // bucket depth = 1 << block_bits: 16 (q5) .. 256 (q9, and lgwin <= 16)
         case 16:
-          if (shallow_match) k_match_shallow<16><<<mgrid, MATCH_THREADS, smem_sh, stream>>>(ma);
+          if (shallow_match) k_match_shallow<16><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
           else k_match<16><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
           break;
         case 32:
-          if (shallow_match) k_match_shallow<32><<<mgrid, MATCH_THREADS, smem_sh, stream>>>(ma);
+          if (shallow_match) k_match_shallow<32><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
           else k_match<32><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
           break;
         case 64: k_match_deep<64><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;

@@ -211,10 +211,11 @@ struct SortArgs {
 };
 
 #define BRO_HASH_LEVEL0 100  // hash_type 100 + l: the long-prefix level l of quality 10 / 11 (bro_hq.cuh: 8, 16, 32 bytes)
+template <bool LEVEL>
 __device__ __forceinline__ uint32_t smem_key(const uint32_t* sw, uint32_t e, int hash_type, int key_bits) {
   // bytes e..e+7 of the tile staged as little-endian words
   const uint32_t sh = (e & 3u) * 8u;
-  if (hash_type >= BRO_HASH_LEVEL0) {
+  if (LEVEL) {
     const uint32_t* q = sw + (e >> 2);
     const uint64_t h = hq_level_hash_with([q, sh](uint32_t k) {
       const uint32_t w0 = q[k >> 2], w1 = q[(k >> 2) + 1], w2 = q[(k >> 2) + 2];
@@ -234,6 +235,7 @@ __device__ __forceinline__ void sort_stage_tile(const SortArgs& a, uint32_t tile
   tma_stage_tile(sw, a.data + (size_t)tile * SORT_TILE, SORT_TILE + 48, bar);
 }
 
+template <bool LEVEL>
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(SortArgs a) {
   __shared__ __align__(16) uint32_t sw[SORT_TILE / 4 + 12];
   __shared__ __align__(8) uint64_t s_bar;
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(SortArgs a) {
     uint32_t e = r * SORT_THREADS + threadIdx.x;
     if (base + e < a.count) {
       uint32_t digit;
-      if (a.pass == 0) digit = smem_key(sw, e, a.hash_type, a.key_bits) & 0xFFu;
+      if (a.pass == 0) digit = smem_key<LEVEL>(sw, e, a.hash_type, a.key_bits) & 0xFFu;
       else digit = a.in[base + e] >> 25;
       atomicAdd(&sh[digit], 1u);
     }
@@ -298,6 +300,7 @@ __global__ void __launch_bounds__(256) k_scan_digits(const uint32_t* totals, uin
   digit_base[threadIdx.x] = s[threadIdx.x];
 }
 
+template <bool LEVEL>
 __global__ void __launch_bounds__(SORT_THREADS, 6) k_sort_scatter(SortArgs a) {
   __shared__ __align__(16) uint32_t sw[SORT_TILE / 4 + 12];
   __shared__ __align__(8) uint64_t s_bar;
@@ -319,7 +322,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 6) k_sort_scatter(SortArgs a) {
     uint32_t digit = 0x100u, w = 0;
     if (valid) {
       if (a.pass == 0) {
-        const uint32_t key = smem_key(sw, e, a.hash_type, a.key_bits);
+        const uint32_t key = smem_key<LEVEL>(sw, e, a.hash_type, a.key_bits);
         digit = key & 0xFFu;
         w = ((key >> 8) << 25) | (base + e);
       } else {
@@ -562,11 +565,12 @@ template <int DEPTH>
 __global__ void __launch_bounds__(MATCH_THREADS) k_match_shallow(MatchArgs a) {
   extern __shared__ __align__(16) uint32_t smem[];
   constexpr uint32_t E = MATCH_THREADS + (uint32_t)DEPTH;
-  // per entry one 16-byte record (position, key, first two data words): the inner loop reads it with a single LDS.128
-  uint4* s_ent = reinterpret_cast<uint4*>(smem);
+  uint32_t* s_pos = smem;
+  uint32_t* s_key = smem + E;
+  uint32_t* s_d0 = smem + 2 * E;
+  uint32_t* s_d1 = smem + 3 * E;
   uint32_t* s_d2 = smem + 4 * E;
   uint32_t* s_d3 = smem + 5 * E;
-  uint32_t* s_pos = smem + 5 * E + E;  // staging area of the TMA copy (E words, 16-byte aligned: E is a multiple of 4)
   const int64_t j0 = (int64_t)blockIdx.x * MATCH_THREADS - DEPTH;
   __shared__ __align__(8) uint64_t s_bar;
   match_stage_positions(a, j0, E, s_pos, &s_bar);
@@ -577,29 +581,27 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_shallow(MatchArgs a) {
       load16_unaligned(a.data + a.origin + pos, w);
       key = hash_key_from_words(a.hash_type, a.key_bits, w[0], w[1]);
     }
-    s_ent[i] = make_uint4(pos, key, w[0], w[1]); s_d2[i] = w[2]; s_d3[i] = w[3];
+    s_key[i] = key; s_d0[i] = w[0]; s_d1[i] = w[1]; s_d2[i] = w[2]; s_d3[i] = w[3];
   }
   __syncthreads();
   const uint32_t i = threadIdx.x + (uint32_t)DEPTH;
-  const uint4 me = s_ent[i];
-  const uint32_t prel = me.x;
+  const uint32_t prel = s_pos[i];
   if (prel == 0xFFFFFFFFu || prel < a.payload_begin) return;
   const uint32_t p = a.origin + prel;
   const uint32_t maxl = bmin(a.lcap, a.n - p);
   uint32_t best_score = BRO_MIN_SCORE, best_len = 0, best_dist = 0;
   if (a.n - p >= 8) {  // keys of the last 7 positions would depend on bytes past the range: they get no bucket match
-    const uint32_t key = me.y;
+    const uint32_t key = s_key[i];
     const uint32_t max_backward = bmin(p, a.max_backward);
-    const uint32_t m0 = me.z, m1 = me.w, m2 = s_d2[i], m3 = s_d3[i];
+    const uint32_t m0 = s_d0[i], m1 = s_d1[i], m2 = s_d2[i], m3 = s_d3[i];
     for (uint32_t cbase = 0; cbase < (uint32_t)DEPTH; cbase += 16) {
       uint32_t mask8 = 0;
 #pragma unroll
       for (uint32_t c = 0; c < 16; ++c) {
         const uint32_t ci = i - 1u - cbase - c;
-        const uint4 ce = s_ent[ci];
-        const uint32_t backward = prel - ce.x;
-        const uint32_t x1 = ce.w ^ m1;
-        const bool ok = (ce.y == key) & (ce.z == m0) & (backward <= max_backward);
+        const uint32_t backward = prel - s_pos[ci];
+        const uint32_t x1 = s_d1[ci] ^ m1;
+        const bool ok = (s_key[ci] == key) & (s_d0[ci] == m0) & (backward <= max_backward);
         mask8 |= (uint32_t)(ok & (x1 == 0u)) << c;
         const uint32_t len = 4u + ((uint32_t)(__ffs((int)x1) - 1) >> 3);  // 4..7 when x1 != 0
         const uint32_t score = score_regular(5, len, backward | 1u);      // H5 / H6 share the score; |1 keeps log2 defined
@@ -613,7 +615,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_shallow(MatchArgs a) {
         const uint32_t c = (uint32_t)__ffs((int)mask8) - 1u;
         mask8 &= mask8 - 1u;
         const uint32_t ci = i - 1u - cbase - c;
-        const uint32_t backward = prel - s_ent[ci].x;
+        const uint32_t backward = prel - s_pos[ci];
         uint32_t len;
         uint32_t x = s_d2[ci] ^ m2;
         if (x) len = 8 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
@@ -638,12 +640,12 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_shallow(MatchArgs a) {
         if (len == maxl) break;  // nothing farther in this group can be better
       }
       if (best_len == maxl) break;  // nor in an older group
-      if (s_ent[i - 16u - cbase].y != key) break;  // the bucket ended inside this group
+      if (s_key[i - 16u - cbase] != key) break;  // the bucket ended inside this group
     }
   }
   uint32_t outv = best_len ? ((best_dist << 8) | best_len) : 0u;
   if (best_len == 0 && a.use_dict && a.n - p >= 8)  // nothing in the bucket: static dictionary (mod.rs:1797, :1942)
-    outv = dict_candidate_dev(a.dict, a.hash_type, me.z, me.w, s_d2[i], s_d3[i], a.data + p, a.n - p, bmin(p, a.max_backward));
+    outv = dict_candidate_dev(a.dict, a.hash_type, s_d0[i], s_d1[i], s_d2[i], s_d3[i], a.data + p, a.n - p, bmin(p, a.max_backward));
   __stcs(&a.best[p], outv);  // scattered, written once, read much later by the parse: do not let it displace the input in L2
 }
 

@@ -171,11 +171,19 @@ __global__ void __launch_bounds__(32) k_zopfli(Workspace W, ZopfliArgs Z, uint32
   U.data = W.data; U.ustart = s; U.len = e - s; U.abs_base = P.abs_base; U.max_backward = P.max_backward; U.quality = P.quality;
   U.model = model; U.lit_pre = pre; U.start_dc = start_dc; U.nodes = Z.nodes + (size_t)u * (P.unit + 1);
   hq_model_initial(model, W.lut);
+  RawCmd* out = W.raw + (size_t)u * (P.unit / 2 + 1);
+  int32_t warm_dc[4];
   {
     const uint32_t mb_span = P.unit * P.mb_units, mb_lo = s / mb_span * mb_span, mb_hi = bmin(P.n, mb_lo + mb_span);
+    if (P.hq_warm && (u % P.mb_units) != 0 && s >= HQ_WARMUP_BYTES) {  // incoming distance cache (bro_hq.cuh:hq_warm_start_cache)
+      HqUnit V = U;
+      V.ustart = s - HQ_WARMUP_BYTES; V.len = HQ_WARMUP_BYTES;
+      hq_literal_costs_unit(W.data + V.ustart, V.len, V.ustart - mb_lo, mb_hi - s, W.lut, hist, pre);
+      hq_warm_start_cache(V, W.hqm, W.hqn, out, warm_dc);
+      U.start_dc = warm_dc;
+    }
     hq_literal_costs_unit(W.data + s, U.len, s - mb_lo, mb_hi - e, W.lut, hist, pre);
   }
-  RawCmd* out = W.raw + (size_t)u * (P.unit / 2 + 1);
   const bool two = P.quality >= 11;
   uint32_t tail, ncopy, ncmd;
   if (two) for (uint32_t i = 0; i < 256 + 704 + 64; ++i) stats[i] = 0;

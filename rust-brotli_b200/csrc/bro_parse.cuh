@@ -42,6 +42,7 @@ struct EncParams {
   int use_dict;       // static-dictionary matches on/off
   int hq_split;       // quality >= 10: 1 = BrotliSplitBlock + clustered context maps (default), 0 = the greedy splitter of q5..q9
   int hq_levels;      // quality >= 10: number of long-prefix candidate levels (8, 16, 32 bytes) on top of the 4-byte buckets: 0..3
+  int hq_warm;        // quality >= 10: parse units learn their incoming distance cache from the HQ_WARMUP_BYTES in front of them
 };
 
 // ---- scores ----
