@@ -117,7 +117,7 @@ struct B200Encoder {
   int num_lanes = 4;
   int ondemand = 1;       // q7..q9: search deep buckets where the parse stands (1) or for every position up front (0, A/B)
   int pair_parse = 4;     // parse units per warp for q5 / q6: 4 (default) or 2; 0 = one unit per warp (kept for A/B measurements)
-  int shallow_match = 1;  // branch-free candidate scan for depth 16 / 32 (0: loop version, kept for A/B measurements)
+  int shallow_match = 1;  // (the loop version of the depth 16 / 32 scan is gone; the option is accepted and ignored)
   Lane lanes[kMaxLanes];
   cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams
   DevBuf d_dict_words, d_dict_hash, d_dict_lutb, d_dict_lute, d_dict_trg, d_dict_tr;
@@ -570,12 +570,10 @@ struct B200Encoder {
       } else
       switch (P.depth) {  // bucket depth = 1 << block_bits: 16 (q5) .. 256 (q9, and lgwin <= 16)
         case 16:
-          if (shallow_match) k_match_shallow<16><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
-          else k_match<16><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
+          k_match_shallow<16><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
           break;
         case 32:
-          if (shallow_match) k_match_shallow<32><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
-          else k_match<32><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
+          k_match_shallow<32><<<mgrid, MATCH_THREADS, smem, stream>>>(ma);
           break;
         case 64: k_match_deep<64><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
         case 128: k_match_deep<128><<<mgrid, MATCH_THREADS, smem, stream>>>(ma); break;
@@ -606,9 +604,7 @@ struct B200Encoder {
       else { B200_OD_LAUNCH(16) }
 #undef B200_OD_LAUNCH
     } else
-    if (pair_parse == 32 && P.n_last == 4 && P.hash_type != 9)  // one unit per thread (q5, q6)
-      k_parse_thread<<<(W.num_units + PARSE_THREAD_BLOCK - 1) / PARSE_THREAD_BLOCK, PARSE_THREAD_BLOCK, 0, stream>>>(W);
-    else if (pair_parse == 4 && P.n_last == 4 && P.hash_type != 9)  // four units per warp (q5, q6)
+    if (pair_parse == 4 && P.n_last == 4 && P.hash_type != 9)  // four units per warp (q5, q6)
       k_parse_pair<4><<<(W.num_units + 4 * PARSE_WARPS - 1) / (4 * PARSE_WARPS), PARSE_WARPS * 32, 0, stream>>>(W);
     else if (pair_parse && P.n_last == 4 && P.hash_type != 9)  // two units per warp
       k_parse_pair<2><<<(W.num_units + 2 * PARSE_WARPS - 1) / (2 * PARSE_WARPS), PARSE_WARPS * 32, 0, stream>>>(W);

@@ -468,94 +468,6 @@ __device__ __forceinline__ void match_stage_positions(const MatchArgs& a, int64_
 }
 
 // dynamic shared memory: (MATCH_THREADS + depth) entries x 6 words.
-// Loop version: one position per lane walks its surviving candidates, nearest first (the direct form of the reference's
-// bucket walk).  Kept as the A/B baseline of k_match_shallow (B200_OPT_SHALLOW_MATCH = 0); deep buckets use k_match_deep.
-// DEPTH = bucket depth (compile time: every shared-memory array offset becomes an immediate).
-template <int DEPTH>
-__global__ void __launch_bounds__(MATCH_THREADS) k_match(MatchArgs a) {
-  extern __shared__ __align__(16) uint32_t smem[];
-  constexpr uint32_t E = MATCH_THREADS + (uint32_t)DEPTH;
-  uint32_t* s_pos = smem;
-  uint32_t* s_key = smem + E;
-  uint32_t* s_d0 = smem + 2 * E;
-  uint32_t* s_d1 = smem + 3 * E;
-  uint32_t* s_d2 = smem + 4 * E;
-  uint32_t* s_d3 = smem + 5 * E;
-  const int64_t j0 = (int64_t)blockIdx.x * MATCH_THREADS - DEPTH;  // sorted index of smem entry 0
-  __shared__ __align__(8) uint64_t s_bar;
-  match_stage_positions(a, j0, E, s_pos, &s_bar);
-  for (uint32_t i = threadIdx.x; i < E; i += MATCH_THREADS) {
-    const uint32_t pos = s_pos[i];
-    uint32_t key = 0xFFFFFFFFu, w[4] = {0, 0, 0, 0};
-    if (pos != 0xFFFFFFFFu) {
-      load16_unaligned(a.data + a.origin + pos, w);
-      key = hash_key_from_words(a.hash_type, a.key_bits, w[0], w[1]);
-    }
-    s_key[i] = key; s_d0[i] = w[0]; s_d1[i] = w[1]; s_d2[i] = w[2]; s_d3[i] = w[3];
-  }
-  __syncthreads();
-  const uint32_t i = threadIdx.x + (uint32_t)DEPTH;
-  const uint32_t prel = s_pos[i];
-  if (prel == 0xFFFFFFFFu || prel < a.payload_begin) return;
-  const uint32_t p = a.origin + prel;
-  const uint32_t maxl = bmin(a.lcap, a.n - p);
-  uint32_t best_score = BRO_MIN_SCORE, best_len = 0, best_dist = 0;
-  if (a.n - p >= 8) {  // keys of the last 7 positions would depend on bytes past the range: they get no bucket match
-    const uint32_t key = s_key[i];
-    const uint32_t max_backward = bmin(p, a.max_backward);
-    const uint32_t m0 = s_d0[i], m1 = s_d1[i], m2 = s_d2[i], m3 = s_d3[i];
-    bool done = false;
-    for (uint32_t cbase = 0; cbase < (uint32_t)DEPTH && !done; cbase += 16) {
-      // phase 1 (branch-free, unrolled): which of the next 16 older entries share the bucket key and the first 4 bytes
-      uint32_t mask = 0;
-#pragma unroll
-      for (uint32_t c = 0; c < 16; ++c) {
-        const uint32_t ci = i - 1u - cbase - c;
-        mask |= (uint32_t)((s_key[ci] == key) & (s_d0[ci] == m0)) << c;
-      }
-      if (s_key[i - 16u - cbase] != key) done = true;  // the bucket ends inside this group: nothing older can match
-      // phase 2: full evaluation of the survivors, nearest first
-      while (mask) {
-        const uint32_t c = (uint32_t)__ffs((int)mask) - 1u;
-        mask &= mask - 1u;
-        const uint32_t ci = i - 1u - cbase - c;
-        const uint32_t backward = prel - s_pos[ci];
-        if (backward > max_backward) { done = true; break; }
-        uint32_t len;
-        uint32_t x = s_d1[ci] ^ m1;
-        if (x) len = 4 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
-        else {
-          x = s_d2[ci] ^ m2;
-          if (x) len = 8 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
-          else {
-            x = s_d3[ci] ^ m3;
-            if (x) len = 12 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
-            else {
-              len = 16;
-              const uint8_t* pa = a.data + p;
-              const uint8_t* pb = pa - backward;
-              while (len + 8 <= maxl) {
-                const uint64_t y = ldu64(pa + len) ^ ldu64(pb + len);
-                if (y) { len += (uint32_t)(__ffsll((long long)y) - 1) >> 3; break; }
-                len += 8;
-              }
-              if (len + 8 > maxl) while (len < maxl && pa[len] == pb[len]) ++len;
-            }
-          }
-        }
-        if (len > maxl) len = maxl;
-        const uint32_t score = score_regular(a.hash_type, len, backward);
-        if (score > best_score) { best_score = score; best_len = len; best_dist = backward; }
-        if (len == maxl) { done = true; break; }
-      }
-    }
-  }
-  uint32_t outv = best_len ? ((best_dist << 8) | best_len) : 0u;
-  if (best_len == 0 && a.use_dict && a.n - p >= 8)  // nothing in the bucket: static dictionary (mod.rs:1797, :1942)
-    outv = dict_candidate_dev(a.dict, a.hash_type, s_d0[i], s_d1[i], s_d2[i], s_d3[i], a.data + p, a.n - p, bmin(p, a.max_backward));
-  a.best[p] = outv;
-}
-
 // Shallow buckets (depth 16 / 32: q5, q6) -- the bench path.  ncu on the loop version (profiles/r01n): 53 % of the warp
 // instructions were the divergent per-survivor loop (23 of 32 lanes active, ~11 rounds per warp).  Here every candidate
 // whose match is shorter than 8 bytes -- the bulk on text -- is resolved branch-free inside the unrolled scan (its length
@@ -1341,170 +1253,6 @@ __global__ void __launch_bounds__(PARSE_WARPS * 32, 10) k_parse_pair(Workspace W
     W.unit_tail[u] = tail_out;
     W.unit_ncopy[u] = ncopy_out;
   }
-}
-
-// One parse unit per THREAD (q5 / q6).  The lane-parallel kernels above spend most of their issue slots keeping 8..32 lanes in
-// step around a walk that is sequential by nature; here every thread simply runs parse_range() for its own unit, written as a
-// three-phase state machine so that the 32 units of a warp never wait for each other's rare long paths:
-//   PROBE   one position q (pos, or pos + 1 while a match is pending): first 8 bytes of the 4 cached distances and the bucket
-//           candidate of best[q]; candidates that are not finished by those 8 bytes (or that were capped by the match stage) are
-//           flagged,
-//   EXTEND  one flagged candidate grows by up to 8 bytes per turn (other threads meanwhile go on with their own phases),
-//   DECIDE  the fold of find_match() (highest score, lowest cache index on ties; the bucket candidate must be strictly better)
-//           and the greedy / lazy step of parse_range().
-// A warp retires 32 probes per ~200 instructions instead of 2..8; what it pays is memory divergence (every load touches 32
-// lines), which is why loads are few and wide.
-__device__ __forceinline__ uint64_t ld8_unaligned(const uint8_t* p) {  // 2 aligned 8-byte loads instead of 3 4-byte loads
-  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  const uint2* q = reinterpret_cast<const uint2*>(a & ~(uintptr_t)7);
-  const uint2 v0 = __ldg(q), v1 = __ldg(q + 1);
-  const bool up = (a & 4u) != 0;
-  const uint32_t w0 = up ? v0.y : v0.x, w1 = up ? v1.x : v0.y, w2 = up ? v1.y : v1.x;
-  const uint32_t sh = (uint32_t)(a & 3u) * 8u;
-  return ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
-}
-
-#ifndef PARSE_THREAD_BLOCK
-#define PARSE_THREAD_BLOCK 32
-#endif
-__global__ void __launch_bounds__(PARSE_THREAD_BLOCK) k_parse_thread(Workspace W) {
-  const uint32_t u = blockIdx.x * PARSE_THREAD_BLOCK + threadIdx.x;
-  if (u >= W.num_units) return;
-  const EncParams& P = W.P;
-  const uint8_t* __restrict__ data = W.data;
-  const uint32_t* __restrict__ best = W.best;
-  const uint32_t s = u * P.unit, e = bmin(P.n, s + P.unit);
-  uint32_t* const out_w = reinterpret_cast<uint32_t*>(W.raw + (size_t)u * (P.unit / 2 + 1));
-  const uint32_t htl = P.hash_type == 6 ? 8u : 4u;
-  const uint32_t window = 64u;
-  const bool D = P.use_dict != 0;
-  const bool near_start = P.abs_base < P.max_backward;
-  const uint32_t lcap = P.lcap;
-  const bool warm = (u % P.mb_units) != 0 && s >= BRO_WARMUP_BYTES;
-  int stage = warm ? 0 : 1;  // 0 warm-up in front of the unit, 1 the unit, 2 done
-  uint32_t pos = stage == 0 ? s - BRO_WARMUP_BYTES : s, uend = stage == 0 ? s : e;
-  uint32_t insert_len = 0, ncmd = 0, copied = 0, arh = pos + window;
-  bool have_m = false;
-  uint32_t m_len = 0, m_dist = 0, m_score = 0;
-  int delayed = 0;
-  int32_t dc0 = 0x3fffffff, dc1 = 0x3fffffff, dc2 = 0x3fffffff, dc3 = 0x3fffffff;
-  uint32_t tail_out = 0, ncopy_out = 0, ncmd_out = 0;
-  auto advance = [&]() {
-    if (stage < 2 && !(have_m || pos + htl < uend)) {
-      if (stage == 1) { tail_out = insert_len + (uend - pos); ncopy_out = copied; ncmd_out = ncmd; stage = 2; }
-      else { stage = 1; pos = s; uend = e; insert_len = 0; ncmd = 0; copied = 0; arh = s + window; }
-    }
-  };
-  advance();
-  advance();
-  enum { PROBE = 0, EXTEND = 1, DECIDE = 2 };
-  int phase = PROBE;
-  uint32_t q = 0, maxl = 0, mb = 0, ext = 0, b = 0, bdist = 0;
-  uint32_t l0 = 0, l1 = 0, l2 = 0, l3 = 0, l4 = 0;
-  while (stage < 2) {
-    if (phase == PROBE) {
-      q = pos + (have_m ? 1u : 0u);
-      maxl = uend - q;
-      mb = near_start ? bmin(q + P.abs_base, P.max_backward) : P.max_backward;
-      const uint64_t c = ld8_unaligned(data + q);
-      b = __ldg(best + q);
-      ext = 0;
-      const uint32_t cap8 = bmin(8u, maxl);
-      auto probe = [&](int32_t back, uint32_t bit) -> uint32_t {
-        const bool ok = back > 0 && (uint32_t)back <= mb;
-        const uint64_t x = c ^ ld8_unaligned(data + q - (ok ? (uint32_t)back : 0u));
-        uint32_t l = x ? ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : 8u;
-        l = bmin(l, cap8);
-        if (ok && l == 8u && maxl > 8u) ext |= bit;
-        return ok ? l : 0u;
-      };
-      l0 = probe(dc0, 1u);
-      l1 = probe(dc1, 2u);
-      l2 = probe(dc2, 4u);
-      l3 = probe(dc3, 8u);
-      l4 = 0;
-      bdist = b >> 8;
-      if (!(b & BRO_BEST_DICT) && (b & 0xFFu) != 0) {
-        const uint32_t blen = b & 0xFFu;
-        l4 = bmin(blen, maxl);
-        if (blen >= lcap && maxl > l4) ext |= 16u;
-      }
-      phase = ext ? EXTEND : DECIDE;
-    }
-    if (phase == EXTEND) {
-      const uint32_t k = (uint32_t)__ffs((int)ext) - 1u;
-      const uint32_t back = k == 0 ? (uint32_t)dc0 : (k == 1 ? (uint32_t)dc1 : (k == 2 ? (uint32_t)dc2 : (k == 3 ? (uint32_t)dc3 : bdist)));
-      uint32_t l = k == 0 ? l0 : (k == 1 ? l1 : (k == 2 ? l2 : (k == 3 ? l3 : l4)));
-      const uint8_t* pa = data + q + l;
-      const uint64_t x = ld8_unaligned(pa) ^ ld8_unaligned(pa - back);
-      const uint32_t mism = x ? ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : 8u;
-      l += bmin(mism, maxl - l);
-      if (mism < 8u || l >= maxl) ext &= ext - 1u;
-      if (k == 0) l0 = l; else if (k == 1) l1 = l; else if (k == 2) l2 = l; else if (k == 3) l3 = l; else l4 = l;
-      if (!ext) phase = DECIDE;
-    }
-    if (phase == DECIDE) {
-      phase = PROBE;
-      uint32_t key = 0;
-      if (l0 >= 2u) key = (score_last_distance(5, l0, 0) << 2) | 3u;
-      if (l1 >= 2u) key = max(key, (score_last_distance(5, l1, 1) << 2) | 2u);
-      if (l2 >= 3u) key = max(key, (score_last_distance(5, l2, 2) << 2) | 1u);
-      if (l3 >= 3u) key = max(key, (score_last_distance(5, l3, 3) << 2) | 0u);
-      bool f_found = key != 0;
-      const uint32_t wi = 3u - (key & 3u);
-      uint32_t f_len = f_found ? (wi == 0 ? l0 : (wi == 1 ? l1 : (wi == 2 ? l2 : l3))) : 0u;
-      uint32_t f_dist = f_found ? (uint32_t)(wi == 0 ? dc0 : (wi == 1 ? dc1 : (wi == 2 ? dc2 : dc3))) : 0u;
-      uint32_t f_score = f_found ? (key >> 2) : BRO_MIN_SCORE;
-      if (b & BRO_BEST_DICT) {
-        Match dm;
-        if (!f_found && D && dict_decode(b, 5, maxl, mb, &dm)) { f_found = true; f_len = dm.len; f_dist = dm.dist; f_score = dm.score; }
-      } else if (l4 >= 4u) {
-        const uint32_t score = score_regular(5, l4, bdist);
-        if (f_score < score) { f_score = score; f_len = l4; f_dist = bdist; f_found = true; }
-      }
-      bool accept = false;
-      if (!have_m) {
-        if (f_found) {
-          m_len = f_len; m_dist = f_dist; m_score = f_score;
-          have_m = true;
-          delayed = 0;
-        } else {
-          insert_len++;
-          pos++;
-          if (pos > arh) {
-            const uint32_t margin = bmax(htl - 1u, 4u);
-            if (pos + 16 + margin >= uend) { insert_len += uend - pos; pos = uend; }
-            else if (pos > arh + 4 * window) { insert_len += 16; pos += 16; }
-            else { insert_len += 8; pos += 8; }
-          }
-        }
-      } else {
-        accept = true;
-        if (f_found && f_score >= m_score + 175u) {
-          pos++;
-          insert_len++;
-          m_len = f_len; m_dist = f_dist; m_score = f_score;
-          if (++delayed < 4 && pos + htl < uend) accept = false;
-        }
-      }
-      if (accept) {
-        const uint32_t m_bytes = len_bytes(m_len);
-        arh = pos + 2 * m_bytes + window;
-        if (!len_is_dict(m_len) && (int32_t)m_dist != dc0) { dc3 = dc2; dc2 = dc1; dc1 = dc0; dc0 = (int32_t)m_dist; }
-        if (stage == 1) { out_w[3u * ncmd] = insert_len; out_w[3u * ncmd + 1u] = m_len; out_w[3u * ncmd + 2u] = m_dist; }
-        ++ncmd;
-        insert_len = 0;
-        copied += m_bytes;
-        pos += m_bytes;
-        have_m = false;
-      }
-      advance();
-      advance();
-    }
-  }
-  W.unit_ncmd[u] = ncmd_out;
-  W.unit_tail[u] = tail_out;
-  W.unit_ncopy[u] = ncopy_out;
 }
 
 // ---------------------------------------------------------------------------------------------------

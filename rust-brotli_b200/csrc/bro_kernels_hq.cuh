@@ -806,12 +806,13 @@ __global__ void __launch_bounds__(1024) k_bs_blocks(Workspace W, BsWs B) {
     const uint32_t ex = block_excl_scan_1024(flag, s_warp, &tot);
     if (flag) {
       const uint32_t b = run + ex;
-      if (b < c.maxb) c.bstart[b] = i;
+      if (b + 1u < c.maxb) c.bstart[b] = i;  // (bstart has maxb words per category and needs one for the end marker)
     }
     run += tot;
   }
   if (threadIdx.x == 0) {
-    const uint32_t nb = bmin(run, c.maxb);
+    // more blocks than the workspace holds (never seen: the switch cost keeps blocks hundreds of symbols long): the tail is one block
+    const uint32_t nb = bmin(run, c.maxb - 1u);
     c.bstart[nb] = t.count;
     c.meta->nb = nb;
   }
