@@ -420,15 +420,15 @@ struct B200Encoder {
     CUDA_OK(cudaMemsetAsync(B.bh_in, 0, (size_t)NM * B.bh_sum * 4, st));
     k_bs_bhist<<<gx3, 256, 0, st>>>(W, B);
     k_bs_cl_prepare<<<gx3, CL_WARPS * 32, 0, st>>>(W, B);
-    k_bs_cl_batch<<<dim3(32, NM, 3), CL_WARPS * 32, 0, st>>>(W, B);
-    k_bs_cl_final<<<g3, 32, 0, st>>>(W, B);
+    k_bs_cl_batch<<<dim3(128, NM, 3), CLB_WARPS * 32, 0, st>>>(W, B);
+    k_bs_cl_final<<<g3, CLB_WARPS * 32, 0, st>>>(W, B);
     k_bs_cl_assign<<<gx3, CL_WARPS * 32, 0, st>>>(W, B);
     k_bs_types<<<g3, 32, 0, st>>>(W, B);
     k_cm_zero<<<dim3(64, NM), 256, 0, st>>>(W, M);
     k_cm_hist<<<gx3, 256, 0, st>>>(W, M);
     k_cm_cl_prepare<<<gx2, CL_WARPS * 32, 0, st>>>(W, M);
-    k_cm_cl_batch<<<gx2, CL_WARPS * 32, 0, st>>>(W, M);
-    k_cm_cl_final<<<g2, 32, 0, st>>>(W, M);
+    k_cm_cl_batch<<<dim3(256, NM, 2), CLB_WARPS * 32, 0, st>>>(W, M);
+    k_cm_cl_final<<<g2, CLB_WARPS * 32, 0, st>>>(W, M);
     k_cm_cl_assign<<<gx2, CL_WARPS * 32, 0, st>>>(W, M);
     k_cm_reindex<<<g2, 256, 0, st>>>(W, M);
     k_cm_rebuild<<<gx2, 256, 0, st>>>(W, M);

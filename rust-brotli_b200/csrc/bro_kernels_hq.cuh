@@ -341,15 +341,53 @@ __device__ void warp_recompute_row(const ClProblem& C, const uint32_t* clusters,
   if ((threadIdx.x & 31) == 0) { C.bj[a] = bj; C.bd[a] = bd; }
   __syncwarp();
 }
-// bs_combine by one warp.  clusters[0..n) ascending ids; symbols[0..nsym) relabelled.  Returns the new count.
-__device__ uint32_t warp_combine(const ClProblem& C, uint32_t* clusters, uint32_t n, uint32_t* symbols, uint32_t nsym, uint32_t max_clusters,
-                                 const uint32_t* lut, uint32_t* s_dh) {
-  const uint32_t lane = threadIdx.x & 31;
+// bs_combine by one CTA of CLB_WARPS warps.  clusters[0..n) ascending ids; symbols[0..nsym) relabelled.  Returns the new count
+// (every thread).  The control flow is CTA uniform; what is spread over the warps is the one expensive thing, the population cost
+// of candidate pairs (a launch list of q10 had this stage, then run by a single warp per problem, at 41 % of all kernel time):
+//   * first fill: row q belongs to warp q % CLB_WARPS,
+//   * after a merge: the rows that only have to look at the new cluster are spread the same way, the rows whose best partner
+//     disappeared are marked and then recomputed one after the other with their partners spread over the warps.
+// A row's best partner is "smallest diff, smallest id on ties" in every variant, so the result does not depend on the mapping.
+#define CLB_WARPS 8
+#define CL_DIRTY 0xFFFFFFFEu
+struct ClbShared {
+  uint32_t dh[CLB_WARPS][18];
+  int64_t red_d[CLB_WARPS];
+  uint32_t red_j[CLB_WARPS];
+};
+__device__ void cta_recompute_row(const ClProblem& C, const uint32_t* clusters, uint32_t n, uint32_t a, const uint32_t* lut, ClbShared& S) {
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t bj = BS_NONE_DEV;
+  int64_t bd = 0;
+  for (uint32_t q = wid; q < n; q += CLB_WARPS) {
+    const uint32_t b = clusters[q];
+    if (b <= a) continue;
+    const int64_t d = warp_pair_diff(C, a, b, lut, S.dh[wid]);
+    if (bj == BS_NONE_DEV || d < bd) { bd = d; bj = b; }
+  }
+  if (lane == 0) { S.red_d[wid] = bd; S.red_j[wid] = bj; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (uint32_t w = 0; w < CLB_WARPS; ++w) {
+      const uint32_t oj = S.red_j[w];
+      if (oj == BS_NONE_DEV) continue;
+      const int64_t od = S.red_d[w];
+      if (bj == BS_NONE_DEV || od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+    }
+    C.bj[a] = bj; C.bd[a] = bd;
+  }
+  __syncthreads();
+}
+__device__ uint32_t cta_combine(const ClProblem& C, uint32_t* clusters, uint32_t n, uint32_t* symbols, uint32_t nsym, uint32_t max_clusters,
+                                const uint32_t* lut, ClbShared& S) {
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (n <= 1) return n;
-  for (uint32_t q = 0; q < n; ++q) warp_recompute_row(C, clusters, n, clusters[q], lut, s_dh);
+  __syncthreads();
+  for (uint32_t q = wid; q < n; q += CLB_WARPS) warp_recompute_row(C, clusters, n, clusters[q], lut, S.dh[wid]);
   bool forced = false;
   while (n > 1) {
-    // best row: smallest diff, then smallest partner distance, then smallest id
+    __syncthreads();
+    // best row: smallest diff, then smallest partner distance, then smallest id (every warp finds the same one)
     uint32_t a = BS_NONE_DEV, ad = 0;
     int64_t abd = 0;
     for (uint32_t q = lane; q < n; q += 32) {
@@ -369,13 +407,14 @@ __device__ uint32_t warp_combine(const ClProblem& C, uint32_t* clusters, uint32_
     if (!forced && abd >= 0) forced = true;
     if (forced && n <= max_clusters) break;
     const uint32_t b = C.bj[a];
-    __syncwarp();
-    for (uint32_t s = lane; s < C.A; s += 32) C.work[(size_t)a * C.A + s] += C.work[(size_t)b * C.A + s];
-    __syncwarp();
-    const uint64_t nc = warp_pop_cost(C.work + (size_t)a * C.A, nullptr, C.A, lut, s_dh);
-    if (lane == 0) { C.cost[a] = nc; C.size[a] += C.size[b]; }
-    for (uint32_t i = lane; i < nsym; i += 32) if (symbols[i] == b) symbols[i] = a;
-    {  // remove b from the list (order preserved)
+    __syncthreads();
+    for (uint32_t s = threadIdx.x; s < C.A; s += CLB_WARPS * 32) C.work[(size_t)a * C.A + s] += C.work[(size_t)b * C.A + s];
+    for (uint32_t i = threadIdx.x; i < nsym; i += CLB_WARPS * 32) if (symbols[i] == b) symbols[i] = a;
+    __syncthreads();
+    const uint64_t nc = warp_pop_cost(C.work + (size_t)a * C.A, nullptr, C.A, lut, S.dh[wid]);  // (every warp, same value)
+    if (wid == 0) {
+      if (lane == 0) { C.cost[a] = nc; C.size[a] += C.size[b]; }
+      // remove b from the list (order preserved)
       uint32_t pos = 0;
       for (uint32_t q0 = 0; q0 < n; q0 += 32) {
         const uint32_t q = q0 + lane;
@@ -390,25 +429,30 @@ __device__ uint32_t warp_combine(const ClProblem& C, uint32_t* clusters, uint32_
         if (q + 1 < n) clusters[q] = v;
         __syncwarp();
       }
-      --n;
     }
-    __syncwarp();
-    for (uint32_t q = 0; q < n; ++q) {
+    --n;
+    __syncthreads();
+    for (uint32_t q = wid; q < n; q += CLB_WARPS) {
       const uint32_t r = clusters[q];
       if (r < a) {
         const uint32_t j = C.bj[r];
-        if (j == a || j == b) warp_recompute_row(C, clusters, n, r, lut, s_dh);
+        if (j == a || j == b) { if (lane == 0) C.bj[r] = CL_DIRTY; }
         else {
-          const int64_t d = warp_pair_diff(C, r, a, lut, s_dh);
+          const int64_t d = warp_pair_diff(C, r, a, lut, S.dh[wid]);
           if (lane == 0 && (j == BS_NONE_DEV || d < C.bd[r] || (d == C.bd[r] && a < j))) { C.bd[r] = d; C.bj[r] = a; }
-          __syncwarp();
         }
       } else if (r > a && r < b) {
-        if (C.bj[r] == b) warp_recompute_row(C, clusters, n, r, lut, s_dh);
+        if (C.bj[r] == b && lane == 0) C.bj[r] = CL_DIRTY;
       }
     }
-    warp_recompute_row(C, clusters, n, a, lut, s_dh);
+    __syncthreads();
+    for (uint32_t q = 0; q < n; ++q) {
+      const uint32_t r = clusters[q];
+      if (r != a && C.bj[r] == CL_DIRTY) cta_recompute_row(C, clusters, n, r, lut, S);
+    }
+    cta_recompute_row(C, clusters, n, a, lut, S);
   }
+  __syncthreads();
   return n;
 }
 
@@ -421,33 +465,35 @@ __device__ __forceinline__ void cl_prepare_one(const ClProblem& C, uint32_t i, c
   const uint64_t c = warp_pop_cost(C.in + (size_t)i * C.A, nullptr, C.A, lut, s_dh);
   if (lane == 0) { C.cost[i] = c; C.size[i] = 1; C.sym[i] = i; }
 }
-// one batch of <= 64 histograms
-__device__ __forceinline__ void cl_batch_one(const ClProblem& C, uint32_t batch, const uint32_t* lut, uint32_t* s_dh) {
-  const uint32_t lane = threadIdx.x & 31;
+// one batch of <= 64 histograms (whole CTA)
+__device__ __forceinline__ void cl_batch_one(const ClProblem& C, uint32_t batch, const uint32_t* lut, ClbShared& S) {
   const uint32_t i0 = batch * 64u, k = bmin(64u, C.n - i0);
-  for (uint32_t j = lane; j < k; j += 32) C.clusters[i0 + j] = i0 + j;
-  __syncwarp();
-  const uint32_t nn = warp_combine(C, C.clusters + i0, k, C.sym + i0, k, C.batch_max, lut, s_dh);
-  if (lane == 0) C.nsurv[batch] = nn;
+  for (uint32_t j = threadIdx.x; j < k; j += CLB_WARPS * 32) C.clusters[i0 + j] = i0 + j;
+  __syncthreads();
+  const uint32_t nn = cta_combine(C, C.clusters + i0, k, C.sym + i0, k, C.batch_max, lut, S);
+  if (threadIdx.x == 0) C.nsurv[batch] = nn;
 }
-// survivors of all batches -> one list, final combine
-__device__ __forceinline__ void cl_final_one(const ClProblem& C, const uint32_t* lut, uint32_t* s_dh) {
+// survivors of all batches -> one list, final combine (whole CTA)
+__device__ __forceinline__ void cl_final_one(const ClProblem& C, const uint32_t* lut, ClbShared& S) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t nbatch = (C.n + 63) / 64;
   uint32_t nc = 0;
-  for (uint32_t b = 0; b < nbatch; ++b) {  // compaction towards the front never overtakes its source
+  for (uint32_t b = 0; b < nbatch; ++b) {  // compaction towards the front never overtakes its source (warp 0 moves, everyone counts)
     const uint32_t k = C.nsurv[b];
-    uint32_t v0 = 0, v1 = 0;
-    if (lane < k) v0 = C.clusters[b * 64u + lane];
-    if (lane + 32 < k) v1 = C.clusters[b * 64u + lane + 32];
-    __syncwarp();
-    if (lane < k) C.clusters[nc + lane] = v0;
-    if (lane + 32 < k) C.clusters[nc + lane + 32] = v1;
-    __syncwarp();
+    if (threadIdx.x < 32) {
+      uint32_t v0 = 0, v1 = 0;
+      if (lane < k) v0 = C.clusters[b * 64u + lane];
+      if (lane + 32 < k) v1 = C.clusters[b * 64u + lane + 32];
+      __syncwarp();
+      if (lane < k) C.clusters[nc + lane] = v0;
+      if (lane + 32 < k) C.clusters[nc + lane + 32] = v1;
+      __syncwarp();
+    }
     nc += k;
   }
-  nc = warp_combine(C, C.clusters, nc, C.sym, C.n, C.final_max, lut, s_dh);
-  if (lane == 0) C.nsurv[-1] = nc;
+  __syncthreads();
+  nc = cta_combine(C, C.clusters, nc, C.sym, C.n, C.final_max, lut, S);
+  if (threadIdx.x == 0) C.nsurv[-1] = nc;
 }
 // bs_best_cluster for input i: nearest of the final clusters, first in list order on ties
 __device__ __forceinline__ void cl_assign_one(const ClProblem& C, uint32_t i, const uint32_t* lut, uint32_t* s_dh) {
@@ -845,24 +891,24 @@ __global__ void __launch_bounds__(CL_WARPS * 32) k_bs_cl_prepare(Workspace W, Bs
   const uint32_t wid = threadIdx.x >> 5;
   for (uint32_t i = blockIdx.x * CL_WARPS + wid; i < C.n; i += gridDim.x * CL_WARPS) cl_prepare_one(C, i, W.lut, s_dh[wid]);
 }
-__global__ void __launch_bounds__(CL_WARPS * 32) k_bs_cl_batch(Workspace W, BsWs B) {
-  __shared__ uint32_t s_dh[CL_WARPS][18];
+// grid (x, num_mb, 3): one CTA per batch of 64 block histograms
+__global__ void __launch_bounds__(CLB_WARPS * 32) k_bs_cl_batch(Workspace W, BsWs B) {
+  __shared__ ClbShared S;
   const uint32_t m = blockIdx.y;
   const int cat = (int)blockIdx.z;
   if (B.meta[(size_t)m * 3 + cat].simple) return;
   const ClProblem C = bs_cluster_problem(W, B, m, cat);
-  const uint32_t wid = threadIdx.x >> 5;
   const uint32_t nbatch = (C.n + 63) / 64;
-  for (uint32_t b = blockIdx.x * CL_WARPS + wid; b < nbatch; b += gridDim.x * CL_WARPS) cl_batch_one(C, b, W.lut, s_dh[wid]);
+  for (uint32_t b = blockIdx.x; b < nbatch; b += gridDim.x) cl_batch_one(C, b, W.lut, S);
 }
-// grid (num_mb, 3), one warp
-__global__ void __launch_bounds__(32) k_bs_cl_final(Workspace W, BsWs B) {
-  __shared__ uint32_t s_dh[18];
+// grid (num_mb, 3), one CTA
+__global__ void __launch_bounds__(CLB_WARPS * 32) k_bs_cl_final(Workspace W, BsWs B) {
+  __shared__ ClbShared S;
   const uint32_t m = blockIdx.x;
   const int cat = (int)blockIdx.y;
   if (B.meta[(size_t)m * 3 + cat].simple) return;
   const ClProblem C = bs_cluster_problem(W, B, m, cat);
-  cl_final_one(C, W.lut, s_dh);
+  cl_final_one(C, W.lut, S);
 }
 __global__ void __launch_bounds__(CL_WARPS * 32) k_bs_cl_assign(Workspace W, BsWs B) {
   __shared__ uint32_t s_dh[CL_WARPS][18];
@@ -1038,17 +1084,16 @@ __global__ void __launch_bounds__(CL_WARPS * 32) k_cm_cl_prepare(Workspace W, Cm
   const uint32_t wid = threadIdx.x >> 5;
   for (uint32_t i = blockIdx.x * CL_WARPS + wid; i < C.n; i += gridDim.x * CL_WARPS) cl_prepare_one(C, i, W.lut, s_dh[wid]);
 }
-__global__ void __launch_bounds__(CL_WARPS * 32) k_cm_cl_batch(Workspace W, CmWs M) {
-  __shared__ uint32_t s_dh[CL_WARPS][18];
+__global__ void __launch_bounds__(CLB_WARPS * 32) k_cm_cl_batch(Workspace W, CmWs M) {
+  __shared__ ClbShared S;
   const ClProblem C = cm_cluster_problem(W, M, blockIdx.y, (int)blockIdx.z);
-  const uint32_t wid = threadIdx.x >> 5;
   const uint32_t nbatch = (C.n + 63) / 64;
-  for (uint32_t b = blockIdx.x * CL_WARPS + wid; b < nbatch; b += gridDim.x * CL_WARPS) cl_batch_one(C, b, W.lut, s_dh[wid]);
+  for (uint32_t b = blockIdx.x; b < nbatch; b += gridDim.x) cl_batch_one(C, b, W.lut, S);
 }
-__global__ void __launch_bounds__(32) k_cm_cl_final(Workspace W, CmWs M) {
-  __shared__ uint32_t s_dh[18];
+__global__ void __launch_bounds__(CLB_WARPS * 32) k_cm_cl_final(Workspace W, CmWs M) {
+  __shared__ ClbShared S;
   const ClProblem C = cm_cluster_problem(W, M, blockIdx.x, (int)blockIdx.y);
-  cl_final_one(C, W.lut, s_dh);
+  cl_final_one(C, W.lut, S);
 }
 __global__ void __launch_bounds__(CL_WARPS * 32) k_cm_cl_assign(Workspace W, CmWs M) {
   __shared__ uint32_t s_dh[CL_WARPS][18];
