@@ -191,7 +191,7 @@ struct B200Encoder {
     uint32_t hint = size_hint > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)size_hint;
     P->size_hint = hint;
     // ChooseHasher, encode.rs:834-893 (H40-42 are not implemented there and fall back to H6 with default params)
-    if (quality >= 10) { P->hash_type = 5; P->key_bits = 15; P->hash_len = 4; P->depth = 1024; P->n_last = 16; }  // bucket lists for k_match_all
+    if (quality >= 10) { P->hash_type = 5; P->key_bits = 15; P->hash_len = 4; P->depth = 256; P->n_last = 16; }  // bucket lists for k_match_all (with the long-prefix levels on, 64..1024 give the same size +-0.02 %)
     else if (quality == 9) { P->hash_type = 9; P->key_bits = 15; P->hash_len = 4; P->depth = 256; P->n_last = 16; }
     else if (lgwin <= 16) { P->hash_type = 6; P->key_bits = 15; P->hash_len = 5; P->depth = 256; P->n_last = 16; }
     else if (hint > (1u << 22) && lgwin >= 19) {
@@ -547,8 +547,9 @@ struct B200Encoder {
         aa.quality = P.quality;
         aa.level = 0;
         aa.last_pass = P.hq_levels == 0;
-        if (P.depth != 1024) { fprintf(stderr, "[brotli_b200] unsupported bucket depth %d\n", P.depth); return false; }
-        k_match_all<1024><<<mgrid, MATCH_THREADS, (size_t)(MATCH_THREADS + 1024) * 3 * 4, stream>>>(aa);
+        if (P.depth == 256) k_match_all<256><<<mgrid, MATCH_THREADS, (size_t)(MATCH_THREADS + 256) * 3 * 4, stream>>>(aa);
+        else if (P.depth == 1024) k_match_all<1024><<<mgrid, MATCH_THREADS, (size_t)(MATCH_THREADS + 1024) * 3 * 4, stream>>>(aa);
+        else { fprintf(stderr, "[brotli_b200] unsupported bucket depth %d\n", P.depth); return false; }
         for (int lv = 0; lv < P.hq_levels; ++lv) {  // long-prefix levels: the batch re-sorted by the level's hash, lists merged
           SortArgs sl = sa;
           sl.hash_type = BRO_HASH_LEVEL0 + lv;

@@ -28,6 +28,23 @@ struct MatchAllArgs {
   int last_pass;    // the pass that adds the static-dictionary matches (they come after every window match)
 };
 
+// First shared-memory index in [lo, i) that is in the bucket `key` and inside the window (position >= min_pos).  The slice is sorted
+// by (key, position), so both bounds are binary searches and the scan loops below test nothing but their filter word.
+__device__ __forceinline__ uint32_t bucket_scan_start(const uint32_t* s_key, const uint32_t* s_pos, uint32_t lo, uint32_t i, uint32_t key,
+                                                     uint32_t min_pos) {
+  uint32_t a = lo, b = i;
+  while (a < b) {
+    const uint32_t mid = (a + b) >> 1;
+    if (s_key[mid] < key) a = mid + 1; else b = mid;
+  }
+  b = i;
+  while (a < b) {
+    const uint32_t mid = (a + b) >> 1;
+    if (s_pos[mid] < min_pos) a = mid + 1; else b = mid;
+  }
+  return a;
+}
+
 template <int DEPTH>
 __global__ void __launch_bounds__(MATCH_THREADS) k_match_all(MatchAllArgs A) {
   extern __shared__ __align__(16) uint32_t smem[];
@@ -63,13 +80,11 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_all(MatchAllArgs A) {
     hq_short_matches(cur, maxl, max_backward, hq_short_back(A.quality), L);
     if (L.best_len < maxl) {
       const uint32_t key = s_key[i], w0 = s_d0[i];
-      for (uint32_t c = 1; c <= (uint32_t)DEPTH; ++c) {
-        const uint32_t ci = i - c;
-        if (s_key[ci] != key) break;  // the bucket starts here
-        const uint32_t backward = prel - s_pos[ci];
-        if (backward > max_backward) break;
+      const uint32_t lo = j0 < 0 ? bmax(i - (uint32_t)DEPTH, (uint32_t)(-j0)) : i - (uint32_t)DEPTH;  // (entries in front of the batch are void)
+      const uint32_t start = bucket_scan_start(s_key, s_pos, lo, i, key, prel > max_backward ? prel - max_backward : 0u);
+      for (uint32_t ci = i; ci-- > start;) {
         if (s_d0[ci] != w0) continue;
-        if (!hq_bucket_candidate(cur, backward, maxl, L)) break;
+        if (!hq_bucket_candidate(cur, prel - s_pos[ci], maxl, L)) break;
       }
     }
     if (a.use_dict && A.last_pass) hq_dict_matches(a.dict, cur, a.n - p, L);
@@ -125,13 +140,11 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_level(MatchAllArgs A) {
     HqMatchList B;
     hq_list_init(B);
     const uint32_t key = s_key[i], chk = s_chk[i];
-    for (uint32_t c = 1; c <= (uint32_t)DEPTH; ++c) {
-      const uint32_t ci = i - c;
-      if (s_key[ci] != key) break;
-      const uint32_t backward = prel - s_pos[ci];
-      if (backward > max_backward) break;
+    const uint32_t lo = j0 < 0 ? bmax(i - (uint32_t)DEPTH, (uint32_t)(-j0)) : i - (uint32_t)DEPTH;
+    const uint32_t start = bucket_scan_start(s_key, s_pos, lo, i, key, prel > max_backward ? prel - max_backward : 0u);
+    for (uint32_t ci = i; ci-- > start;) {
       if (s_chk[ci] != chk) continue;
-      if (!hq_bucket_candidate(cur, backward, maxl, B)) break;
+      if (!hq_bucket_candidate(cur, prel - s_pos[ci], maxl, B)) break;
     }
     hq_merge_lists(L, B);
   }

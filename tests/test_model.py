@@ -39,7 +39,7 @@ def test_model_hq_options(model):
     static dictionary each pay for themselves on English text."""
     d = golden_bytes("asyoulik.txt")
     base = len(model.compress(d, 10, 22)[0])
-    for kw in ({"hq_split": 0}, {"use_dict": 0}, {"ctx_model": 0}, {"unit": 65536, "mb_units": 64}, {"depth": 256}):
+    for kw in ({"hq_split": 0}, {"use_dict": 0}, {"ctx_model": 0}, {"unit": 65536, "mb_units": 64}, {"depth": 1024}):
         c, _ = model.compress(d, 10, 22, **kw)
         assert sys_decompress(c, len(d)) == d
         if "unit" not in kw and "depth" not in kw:
