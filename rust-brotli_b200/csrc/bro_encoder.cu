@@ -112,7 +112,7 @@ struct B200Encoder {
   // configuration knobs (tests flip these)
   uint32_t unit = 4096, mb_units = 1024, lcap = 64;
   int use_rle_opt = 1, split = 1, ctx_model = 1, use_dict = 1, hq_split = 1, hq_levels = HQ_MAX_LEVELS;
-  uint32_t hq_unit = 16384;  // parse unit of the shortest-path parse (quality >= 10)
+  uint32_t hq_unit = 0;  // parse unit of the shortest-path parse (quality >= 10); 0 = 8 KiB at q10, 16 KiB at q11 (measured: DESIGN.md)
   int hq_thread_units = 0;   // 1: one parse unit per thread instead of one per warp (A/B switch)
   int num_lanes = 4;
   int ondemand = 1;       // q7..q9: search deep buckets where the parse stands (1) or for every position up front (0, A/B)
@@ -215,7 +215,7 @@ struct B200Encoder {
     P->hq_warm = 1;
     if (quality >= 10) {  // same metablock span, larger parse units
       const uint32_t span = P->unit * P->mb_units;
-      P->unit = bmin(hq_unit, span);
+      P->unit = bmin(hq_unit ? hq_unit : (quality >= 11 ? 16384u : 8192u), span);
       P->mb_units = span / P->unit;
       P->lcap = HQ_LCAP;
     }
@@ -589,8 +589,10 @@ struct B200Encoder {
       za.nodes = L.d_hq_nodes.as<ZNode>();
       za.pre = L.d_hq_pre.as<uint32_t>();
       za.scratch = L.d_hq_scratch.as<uint32_t>();
-      if (hq_thread_units) k_zopfli<<<(W.num_units + 31) / 32, 32, 0, stream>>>(W, za, 1u);
-      else k_zopfli<<<W.num_units, 32, 0, stream>>>(W, za, 32u);
+      for (int phase = 1; phase <= (P.quality >= 11 ? 2 : 1); ++phase) {
+        if (hq_thread_units) k_zopfli<<<(W.num_units + 31) / 32, 32, 0, stream>>>(W, za, 1u, phase);
+        else k_zopfli<<<W.num_units, 32, 0, stream>>>(W, za, 32u, phase);
+      }
     } else
     if (od) {
       const uint32_t pg = (W.num_units + PARSE_WARPS - 1) / PARSE_WARPS;

@@ -567,6 +567,13 @@ BRO_HD_NOINLINE uint32_t hq_zopfli_unit(const HqUnit& U, const HqMatch* matches,
   return k;
 }
 
+// Quality 11 runs the shortest path twice, the second time with costs taken from the commands of the first pass
+// (set_from_commands, hq.rs:1076-1154).  The reference has one 256 KiB block to take them from; a 8 KiB parse unit alone is too
+// small a sample (+0.7 % on text against +0.37 % for 64 KiB units), so the statistics of the first pass are pooled over the units
+// of one aligned HQ_STATS_SPAN window of the metablock before the second pass starts (two kernels: k_zopfli phase 1 / phase 2).
+#define HQ_STATS_SPAN 65536u
+#define HQ_STATS_WORDS (256u + 704u + 64u)
+
 // Distance cache a parse unit starts with.  Units are parsed independently, so a unit does not know the last distances of its
 // predecessor -- on record-structured input (JSON logs) that costs 0.35 %, because "same distance as before" is the cheapest code
 // there is.  Like the q5..q9 parse (BRO_WARMUP_BYTES) the unit therefore first parses the HQ_WARMUP_BYTES in front of it, keeps the

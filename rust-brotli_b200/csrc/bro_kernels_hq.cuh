@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_level(MatchAllArgs A) {
 // chain of dependent updates; the parallelism is across the units of a chunk).
 // ---------------------------------------------------------------------------------------------------
 #define BS_NONE_DEV 0xFFFFFFFFu
-#define HQ_SCRATCH_WORDS 3072u  // per unit: HqCostModel (769) | literal-cost histograms (768) | pass-1 statistics (1024) | literal costs (256)
+#define HQ_SCRATCH_WORDS 4096u  // per unit: HqCostModel (769) | literal-cost histograms (768) | pass-1 statistics (1024) | literal costs (256) | warm-up cache (4) | pooled statistics (1024)
 
 struct ZopfliArgs {
   ZNode* nodes;       // [num_units][unit + 1]
@@ -166,11 +166,13 @@ struct ZopfliArgs {
   uint32_t* scratch;  // [num_units][HQ_SCRATCH_WORDS]
 };
 
-// lanes_per_unit = 32: one unit per warp (lane 0 works); 1: one unit per thread (32 units per warp: the lanes diverge, but the hot
-// loops -- byte compares, per-length cost updates -- reconverge often enough to beat 31 idle lanes)
-__global__ void __launch_bounds__(32) k_zopfli(Workspace W, ZopfliArgs Z, uint32_t lanes_per_unit) {
+// lanes_per_unit = 32: one unit per warp (lane 0 runs the node sweep); 1: one unit per thread (32 units per warp; slower, kept as a
+// switch).  phase 1: warm-up cache, literal costs, shortest path with the initial cost model; at quality 11 the command statistics
+// stay in the unit's scratch.  phase 2 (quality 11 only): the statistics of the unit's HQ_STATS_SPAN window are pooled (all lanes),
+// costs from them, second shortest path.
+__global__ void __launch_bounds__(32) k_zopfli(Workspace W, ZopfliArgs Z, uint32_t lanes_per_unit, int phase) {
   const uint32_t u = lanes_per_unit == 1 ? blockIdx.x * 32 + threadIdx.x : blockIdx.x;
-  if (u >= W.num_units || (lanes_per_unit != 1 && threadIdx.x != 0)) return;
+  if (u >= W.num_units) return;
   const EncParams& P = W.P;
   const uint32_t s = u * P.unit, e = bmin(P.n, s + P.unit);
   uint32_t* scr = Z.scratch + (size_t)u * HQ_SCRATCH_WORDS;
@@ -178,31 +180,44 @@ __global__ void __launch_bounds__(32) k_zopfli(Workspace W, ZopfliArgs Z, uint32
   uint32_t* hist = scr + 769;
   uint32_t* stats = scr + 769 + 768;
   uint32_t* cost_literal = scr + 769 + 768 + 1024;
+  int32_t* warm_dc = reinterpret_cast<int32_t*>(scr + 769 + 768 + 1024 + 256);
+  uint32_t* pooled = scr + 769 + 768 + 1024 + 256 + 4;
+  if (phase == 2) {  // pool the first-pass statistics of the window (they are complete: phase 1 was a kernel of its own)
+    const uint32_t gu = bmax(1u, HQ_STATS_SPAN / P.unit);
+    const uint32_t mb_u0 = u / P.mb_units * P.mb_units;
+    const uint32_t g0 = mb_u0 + (u - mb_u0) / gu * gu, g1 = bmin(bmin(W.num_units, g0 + gu), mb_u0 + P.mb_units);
+    const uint32_t step = lanes_per_unit == 1 ? 1u : 32u, first = lanes_per_unit == 1 ? 0u : threadIdx.x;
+    for (uint32_t k = first; k < HQ_STATS_WORDS; k += step) {
+      uint32_t acc = 0;
+      for (uint32_t v = g0; v < g1; ++v) acc += Z.scratch[(size_t)v * HQ_SCRATCH_WORDS + 769 + 768 + k];
+      pooled[k] = acc;
+    }
+    if (lanes_per_unit != 1) __syncwarp();
+  }
+  if (lanes_per_unit != 1 && threadIdx.x != 0) return;
   uint32_t* pre = Z.pre + (size_t)u * (P.unit + 1);
-  const int32_t start_dc[4] = {0x3fffffff, 0x3fffffff, 0x3fffffff, 0x3fffffff};
   HqUnit U;
   U.data = W.data; U.ustart = s; U.len = e - s; U.abs_base = P.abs_base; U.max_backward = P.max_backward; U.quality = P.quality;
-  U.model = model; U.lit_pre = pre; U.start_dc = start_dc; U.nodes = Z.nodes + (size_t)u * (P.unit + 1);
+  U.model = model; U.lit_pre = pre; U.start_dc = warm_dc; U.nodes = Z.nodes + (size_t)u * (P.unit + 1);
   hq_model_initial(model, W.lut);
   RawCmd* out = W.raw + (size_t)u * (P.unit / 2 + 1);
-  int32_t warm_dc[4];
-  {
-    const uint32_t mb_span = P.unit * P.mb_units, mb_lo = s / mb_span * mb_span, mb_hi = bmin(P.n, mb_lo + mb_span);
-    if (P.hq_warm && (u % P.mb_units) != 0 && s >= HQ_WARMUP_BYTES) {  // incoming distance cache (bro_hq.cuh:hq_warm_start_cache)
-      HqUnit V = U;
-      V.ustart = s - HQ_WARMUP_BYTES; V.len = HQ_WARMUP_BYTES;
-      hq_literal_costs_unit(W.data + V.ustart, V.len, V.ustart - mb_lo, mb_hi - s, W.lut, hist, pre);
-      hq_warm_start_cache(V, W.hqm, W.hqn, out, warm_dc);
-      U.start_dc = warm_dc;
-    }
-    hq_literal_costs_unit(W.data + s, U.len, s - mb_lo, mb_hi - e, W.lut, hist, pre);
-  }
   const bool two = P.quality >= 11;
   uint32_t tail, ncopy, ncmd;
-  if (two) for (uint32_t i = 0; i < 256 + 704 + 64; ++i) stats[i] = 0;
-  ncmd = hq_zopfli_unit(U, W.hqm, W.hqn, out, &tail, &ncopy, two ? stats : nullptr);
-  if (two) {
-    hq_model_from_stats(model, stats, W.lut, W.data + s, U.len, cost_literal, pre);
+  if (phase == 1) {
+    const uint32_t mb_span = P.unit * P.mb_units, mb_lo = s / mb_span * mb_span, mb_hi = bmin(P.n, mb_lo + mb_span);
+    warm_dc[0] = warm_dc[1] = warm_dc[2] = warm_dc[3] = 0x3fffffff;
+    if (P.hq_warm && (u % P.mb_units) != 0 && s >= HQ_WARMUP_BYTES) {  // incoming distance cache (bro_hq.cuh:hq_warm_start_cache)
+      const int32_t unknown[4] = {0x3fffffff, 0x3fffffff, 0x3fffffff, 0x3fffffff};
+      HqUnit V = U;
+      V.ustart = s - HQ_WARMUP_BYTES; V.len = HQ_WARMUP_BYTES; V.start_dc = unknown;
+      hq_literal_costs_unit(W.data + V.ustart, V.len, V.ustart - mb_lo, mb_hi - s, W.lut, hist, pre);
+      hq_warm_start_cache(V, W.hqm, W.hqn, out, warm_dc);
+    }
+    hq_literal_costs_unit(W.data + s, U.len, s - mb_lo, mb_hi - e, W.lut, hist, pre);
+    if (two) for (uint32_t i = 0; i < HQ_STATS_WORDS; ++i) stats[i] = 0;
+    ncmd = hq_zopfli_unit(U, W.hqm, W.hqn, out, &tail, &ncopy, two ? stats : nullptr);
+  } else {
+    hq_model_from_stats(model, pooled, W.lut, W.data + s, U.len, cost_literal, pre);
     ncmd = hq_zopfli_unit(U, W.hqm, W.hqn, out, &tail, &ncopy, nullptr);
   }
   W.unit_ncmd[u] = ncmd;

@@ -456,12 +456,13 @@ def test_config5_quickfox_tiled_512mib_q11_lgwin24(encoder):
     assert hashlib.sha256(sys_decompress(c, len(d))).digest() == hashlib.sha256(d).digest()
 
 
-@pytest.mark.parametrize("kind,q,bound", [("text", 10, 1.005), ("text", 11, 1.007), ("json", 10, 1.007), ("json", 11, 1.007)])
+@pytest.mark.parametrize("kind,q,bound", [("text", 10, 1.005), ("text", 11, 1.005), ("json", 10, 1.006), ("json", 11, 1.005)])
 def test_hq_multi_metablock_equals_model_and_reference_size(encoder, model, kind, q, bound):
     """quality 10 / 11 on 6 MB of enwik-shaped text and of JSON logs (two metablocks, many parse units): bit identity with the CPU
     model, and size against libbrotlienc (the stated size reference for q >= 10, tests/golden/make_golden.py).  Measured with the
-    three long-prefix candidate levels (bro_hq.cuh): text +0.23 % (q10) / +0.53 % (q11), JSON +0.48 % / +0.54 %; with the 4-byte
-    bucket lists alone it was +1.2 / +1.5 % and +2.0 / +2.7 % (on the reference's own KAT file alice29 it is +0.1 %)."""
+    three long-prefix candidate levels and, at q11, the first-pass statistics pooled over 64 KiB (bro_hq.cuh): text +0.24 % (q10) /
+    +0.43 % (q11), JSON +0.47 % / +0.33 %; with the 4-byte bucket lists alone it was +1.2 / +1.5 % and +2.0 / +2.7 % (on the
+    reference's own KAT file alice29 it is +0.1 %)."""
     import rust_brotli_b200 as rb
     from tools import datagen
     d = datagen.enwik_like(6_000_000) if kind == "text" else datagen.json_logs(6_000_000)
