@@ -1518,7 +1518,7 @@ __device__ __forceinline__ uint32_t parse_range_ondemand(const EncParams& P, con
 }
 
 template <int NL, int DEPTH>
-__global__ void __launch_bounds__(PARSE_WARPS * 32) k_parse_ondemand(Workspace W, DeepArgs A) {
+__global__ void __launch_bounds__(PARSE_WARPS * 32, 8) k_parse_ondemand(Workspace W, DeepArgs A) {
   const uint32_t u = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);
   if (u >= W.num_units) return;
   const EncParams& P = W.P;
