@@ -360,6 +360,7 @@ struct HqUnit {  // everything UpdateNodes needs about the unit being parsed
   const uint32_t* lit_pre; // [len + 1]
   const int32_t* start_dc; // [4]
   ZNode* nodes;            // [len + 1]
+  int coop;                // device only: the whole warp runs this unit in lock step (same data in every lane) and shares the probes
 };
 BRO_HD uint32_t hq_max_distance(const HqUnit& U, uint32_t pos) {
   const uint64_t a = U.abs_base + U.ustart + pos;
@@ -436,13 +437,41 @@ BRO_HD_NOINLINE uint32_t hq_update_nodes(const HqUnit& U, uint32_t pos, const Hq
     const uint32_t inscode = insert_length_code(pos - start);
     const int64_t base_cost = pd.costdiff + ((int64_t)ins_extra(inscode) << HQ_QBITS) + (int64_t)U.lit_pre[pos];
     uint32_t best_len = min_len - 1;
+#ifdef __CUDA_ARCH__
+    // Half of the sweep's instructions were this loop, almost always ending at the first-byte test (profiles/r02ag_ncu_zopfli.txt).
+    // When the warp runs the unit in lock step, lane j probes cached distance j and only the distances that can improve on
+    // min_len - 1 go through the sequential part below, in the same order with the same test: identical nodes.
+    uint32_t coop_hits = 0xFFFFu, coop_len = 0;
+    if (U.coop) {
+      const uint32_t lane = threadIdx.x & 31u;
+      if (lane < 16u && best_len < max_len) {
+        const int32_t bs = cache_candidate(pd.dc, (int)lane);
+        if (bs > 0 && (uint32_t)bs <= max_distance) {
+          const uint8_t* prev = cur - bs;
+          if (cur[best_len] == prev[best_len]) coop_len = hq_lcp(prev, cur, max_len);
+        }
+      }
+      coop_hits = __ballot_sync(0xffffffffu, coop_len > best_len) & 0xFFFFu;
+    }
+#endif
     for (int j = 0; j < 16 && best_len < max_len; ++j) {
+#ifdef __CUDA_ARCH__
+      if (U.coop) {
+        if (!coop_hits) break;
+        j = __ffs((int)coop_hits) - 1;
+        coop_hits &= coop_hits - 1u;
+      }
+#endif
       const int32_t backward_s = cache_candidate(pd.dc, j);  // kDistanceCacheIndex / Offset, mod.rs:653-655
       if (backward_s <= 0 || (uint32_t)backward_s > max_distance) continue;
       const uint32_t backward = (uint32_t)backward_s;
       const uint8_t* prev = cur - backward;
       if (cur[best_len] != prev[best_len]) continue;
+#ifdef __CUDA_ARCH__
+      const uint32_t len = U.coop ? __shfl_sync(0xffffffffu, coop_len, j) : hq_lcp(prev, cur, max_len);
+#else
       const uint32_t len = hq_lcp(prev, cur, max_len);
+#endif
       const int64_t dist_cost = base_cost + M.cost_dist[j];
       for (uint32_t l = best_len + 1; l <= len; ++l) {
         const uint32_t copycode = copy_length_code(l);

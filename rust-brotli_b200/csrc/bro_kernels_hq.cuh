@@ -194,11 +194,13 @@ __global__ void __launch_bounds__(32) k_zopfli(Workspace W, ZopfliArgs Z, uint32
     }
     if (lanes_per_unit != 1) __syncwarp();
   }
-  if (lanes_per_unit != 1 && threadIdx.x != 0) return;
+  // one unit per warp: every lane runs the node sweep on the same data (same loads, same stores: no more issue slots than one
+  // lane would take), so that the 16 distance-cache probes of UpdateNodes can be spread over the lanes (HqUnit::coop)
   uint32_t* pre = Z.pre + (size_t)u * (P.unit + 1);
   HqUnit U;
   U.data = W.data; U.ustart = s; U.len = e - s; U.abs_base = P.abs_base; U.max_backward = P.max_backward; U.quality = P.quality;
   U.model = model; U.lit_pre = pre; U.start_dc = warm_dc; U.nodes = Z.nodes + (size_t)u * (P.unit + 1);
+  U.coop = lanes_per_unit != 1;
   hq_model_initial(model, W.lut);
   RawCmd* out = W.raw + (size_t)u * (P.unit / 2 + 1);
   const bool two = P.quality >= 11;
