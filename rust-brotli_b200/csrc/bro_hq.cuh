@@ -431,6 +431,32 @@ BRO_HD_NOINLINE uint32_t hq_update_nodes(const HqUnit& U, uint32_t pos, const Hq
     min_len = len;
   }
   const uint32_t ncand = bmin((uint32_t)hq_max_candidates(U.quality), hq_queue_size(Q));
+#ifdef __CUDA_ARCH__
+  // Half of the sweep's instructions were the 16 distance-cache probes per start position, almost always ending at the first-byte
+  // test (profiles/r02ag_ncu_zopfli.txt).  When the warp runs the unit in lock step, the (start k, cached distance j) pairs -- up
+  // to 5 x 16 at quality 11 -- are spread over the lanes, three independent rounds whose loads overlap; only the pairs that can
+  // improve on min_len - 1 go through the sequential part below, in the same order with the same test: identical nodes.
+  uint32_t coop_len0 = 0, coop_len1 = 0, coop_len2 = 0, coop_ball0 = 0, coop_ball1 = 0, coop_ball2 = 0;
+  if (U.coop) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t bl0 = min_len - 1;
+#pragma unroll
+    for (uint32_t r = 0; r < 3; ++r) {
+      const uint32_t pidx = lane + 32u * r;
+      uint32_t l = 0;
+      if (pidx < 16u * ncand && bl0 < max_len) {
+        const HqPosData& pq = hq_queue_at(Q, pidx >> 4);
+        const int32_t bs = cache_candidate(pq.dc, (int)(pidx & 15u));
+        if (bs > 0 && (uint32_t)bs <= max_distance) {
+          const uint8_t* prev = cur - bs;
+          if (cur[bl0] == prev[bl0]) l = hq_lcp(prev, cur, max_len);
+        }
+      }
+      const uint32_t ball = __ballot_sync(0xffffffffu, l > bl0);
+      if (r == 0) { coop_len0 = l; coop_ball0 = ball; } else if (r == 1) { coop_len1 = l; coop_ball1 = ball; } else { coop_len2 = l; coop_ball2 = ball; }
+    }
+  }
+#endif
   for (uint32_t k = 0; k < ncand; ++k) {
     const HqPosData& pd = hq_queue_at(Q, k);
     const uint32_t start = pd.pos;
@@ -438,21 +464,10 @@ BRO_HD_NOINLINE uint32_t hq_update_nodes(const HqUnit& U, uint32_t pos, const Hq
     const int64_t base_cost = pd.costdiff + ((int64_t)ins_extra(inscode) << HQ_QBITS) + (int64_t)U.lit_pre[pos];
     uint32_t best_len = min_len - 1;
 #ifdef __CUDA_ARCH__
-    // Half of the sweep's instructions were this loop, almost always ending at the first-byte test (profiles/r02ag_ncu_zopfli.txt).
-    // When the warp runs the unit in lock step, lane j probes cached distance j and only the distances that can improve on
-    // min_len - 1 go through the sequential part below, in the same order with the same test: identical nodes.
-    uint32_t coop_hits = 0xFFFFu, coop_len = 0;
-    if (U.coop) {
-      const uint32_t lane = threadIdx.x & 31u;
-      if (lane < 16u && best_len < max_len) {
-        const int32_t bs = cache_candidate(pd.dc, (int)lane);
-        if (bs > 0 && (uint32_t)bs <= max_distance) {
-          const uint8_t* prev = cur - bs;
-          if (cur[best_len] == prev[best_len]) coop_len = hq_lcp(prev, cur, max_len);
-        }
-      }
-      coop_hits = __ballot_sync(0xffffffffu, coop_len > best_len) & 0xFFFFu;
-    }
+    const uint32_t coop_sh = (k & 1u) * 16u;
+    const uint32_t coop_round_ball = (k >> 1) == 0 ? coop_ball0 : ((k >> 1) == 1 ? coop_ball1 : coop_ball2);
+    const uint32_t coop_len = (k >> 1) == 0 ? coop_len0 : ((k >> 1) == 1 ? coop_len1 : coop_len2);
+    uint32_t coop_hits = (coop_round_ball >> coop_sh) & 0xFFFFu;
 #endif
     for (int j = 0; j < 16 && best_len < max_len; ++j) {
 #ifdef __CUDA_ARCH__
@@ -468,7 +483,7 @@ BRO_HD_NOINLINE uint32_t hq_update_nodes(const HqUnit& U, uint32_t pos, const Hq
       const uint8_t* prev = cur - backward;
       if (cur[best_len] != prev[best_len]) continue;
 #ifdef __CUDA_ARCH__
-      const uint32_t len = U.coop ? __shfl_sync(0xffffffffu, coop_len, j) : hq_lcp(prev, cur, max_len);
+      const uint32_t len = U.coop ? __shfl_sync(0xffffffffu, coop_len, (int)coop_sh + j) : hq_lcp(prev, cur, max_len);
 #else
       const uint32_t len = hq_lcp(prev, cur, max_len);
 #endif
