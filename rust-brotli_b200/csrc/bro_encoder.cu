@@ -478,6 +478,9 @@ struct B200Encoder {
     W.out_cap_bytes = out_cap_bytes;
     const uint8_t* d_all = d_data.as<uint8_t>() - data_base;  // indexable by absolute position >= data_base
     k_init_mb<<<(W.num_mb + 63) / 64, 64, 0, stream>>>(W);
+    // the literal context decision needs the input only: it runs here, under the throughput-bound stages of the other lanes,
+    // instead of in the latency-bound tail of the chunk
+    k_ctx_decide<<<W.num_mb, 256, 0, stream>>>(W);
     // ---- sort + match, batch by batch ----
     const uint32_t window = 1u << P.lgwin;
     const uint32_t payload_max = kBatchMax - window - 4096;
@@ -623,7 +626,6 @@ struct B200Encoder {
       k_dist_apply<<<dim3(64, W.num_mb), 256, 0, stream>>>(W, L.d_dist_cost.as<uint64_t>());
       launches += 2;
     }
-    k_ctx_decide<<<W.num_mb, 256, 0, stream>>>(W);
     {
       dim3 g((W.cmd_cap + 255) / 256, W.num_mb);
       cudaMemsetAsync(W.long_tab, 0, (size_t)W.num_mb * W.long_cap * sizeof(uint2), stream);
