@@ -105,6 +105,23 @@ def test_edge_sizes(encoder, model, n):
     assert c == model.compress(d, 5, 22)[0]
 
 
+@pytest.mark.parametrize("q", [9, 10, 11])
+def test_edge_sizes_deep_and_hq(encoder, model, q):
+    """The sizes that switch something on in the q9 on-demand search (forced) and in the q10 / q11 path: first bucket match, the
+    long-prefix levels (8 + 8 / 16 / 32 bytes), the 512-byte warm-up, 8 / 16 KiB parse units, the 64 KiB statistics window."""
+    import rust_brotli_b200 as rb
+    src = golden_bytes("alice29.txt") * 2
+    encoder.set_option(rb._native.OPT_ONDEMAND, 2)
+    try:
+        for n in (0, 1, 2, 3, 7, 8, 9, 39, 40, 41, 63, 64, 65, 511, 512, 513, 4097, 8191, 8192, 8193, 16383, 16385, 65535, 65537, 70001):
+            d = src[:n]
+            c = encoder.compress(d, q, 22)
+            assert sys_decompress(c, max(n, 1)) == d, n
+            assert c == model.compress(d, q, 22)[0], n
+    finally:
+        encoder.set_option(rb._native.OPT_ONDEMAND, 1)
+
+
 @pytest.mark.parametrize("lgwin", [10, 12, 16, 17, 18, 20, 24])
 def test_window_sizes(encoder, model, lgwin):
     d = golden_bytes("asyoulik.txt") + golden_bytes("alice29.txt")

@@ -182,3 +182,13 @@ def test_catable_framing_stitches_like_brocatli(model, q):
     with pytest.raises(bc.NotCraftedForConcatenation):
         bc.concat([sa, model.compress(b, q, 22)[0]])
     assert bc.window_bits(sa) == (22, 4)
+
+
+@pytest.mark.parametrize("q", [10, 11])
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 7, 8, 9, 39, 40, 41, 63, 64, 65, 511, 512, 513, 8191, 8192, 8193, 16383, 16385, 70001])
+def test_model_hq_edge_sizes(model, q, n):
+    """quality 10 / 11 around every size that switches something on: 8 bytes (first bucket match), 8 + 8 / 16 / 32 bytes (the
+    long-prefix levels), the 512-byte warm-up, the 8 / 16 KiB parse units, the 64 KiB statistics window."""
+    d = (golden_bytes("alice29.txt") * 2)[:n]
+    c, _ = model.compress(d, q, 22)
+    assert sys_decompress(c, max(n, 1)) == d
