@@ -215,7 +215,7 @@ struct B200Encoder {
     P->hq_warm = 1;
     if (quality >= 10) {  // same metablock span, larger parse units
       const uint32_t span = P->unit * P->mb_units;
-      P->unit = bmin(hq_unit ? hq_unit : (quality >= 11 ? 16384u : 8192u), span);
+      P->unit = bmin(hq_unit ? hq_unit : hq_default_unit(quality, hint), span);
       P->mb_units = span / P->unit;
       P->lcap = HQ_LCAP;
     }

@@ -611,6 +611,17 @@ BRO_HD_NOINLINE uint32_t hq_zopfli_unit(const HqUnit& U, const HqMatch* matches,
   return k;
 }
 
+// Parse unit of the shortest-path parse.  A unit is one serial node sweep, so its size is the latency of the whole stage (a 16 KiB
+// unit at quality 11 takes ~0.1 s -- more than a CPU needs for a small file), while many units are needed to fill the machine.
+// Large inputs: 8 KiB at quality 10, 16 KiB at quality 11 (size / speed trade measured in DESIGN.md); inputs known to be small get
+// smaller units: they cannot fill the GPU anyway, the pooled statistics (below) keep the cost model the same, and the size moves
+// by +0.05 ... +0.1 % (alice29 q11: 246 -> 33 ms).  size_hint = 0 means unknown.
+BRO_HD uint32_t hq_default_unit(int quality, uint32_t size_hint) {
+  if (size_hint != 0 && size_hint <= (256u << 10)) return 2048u;
+  if (size_hint != 0 && size_hint <= (1u << 20)) return 4096u;
+  return quality >= 11 ? 16384u : 8192u;
+}
+
 // Quality 11 runs the shortest path twice, the second time with costs taken from the commands of the first pass
 // (set_from_commands, hq.rs:1076-1154).  The reference has one 256 KiB block to take them from; a 8 KiB parse unit alone is too
 // small a sample (+0.7 % on text against +0.37 % for 64 KiB units), so the statistics of the first pass are pooled over the units
